@@ -1,0 +1,129 @@
+// Shared declarations for libst2 (sm_100a only).  See include/st2.h for the C ABI.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/st2.h"
+
+#define ST2_MAX_HIST 11          // L-BFGS: n_corr (10) + one staging slot
+
+// ---- network topology (models/vgg19.prototxt:3-337 of the reference) ------------------------
+enum BlobKind { KIND_INPUT = 0, KIND_CONV = 1, KIND_POOL = 2 };
+struct BlobInfo { const char* name; int kind; int channels; int conv_index; };
+extern const BlobInfo g_blobs[ST2_NUM_BLOBS];
+
+// ---- scalar block layout (doubles, device) ---------------------------------------------------
+// per blob b: base = b * ST2_SCAL_PER_BLOB
+enum {
+  SB_C_SUMSQ = 0,     // sum (F - Fc)^2
+  SB_S_GRAMSQ,        // sum D^2          (D = gram(F) - A)
+  SB_S_RAWSQ,         // sum (D F)^2      (unscaled style gradient)
+  SB_D_SUMSQ,         // sum F^2
+  SB_C_NORM, SB_S_NORM, SB_D_NORM,          // frozen normalisers (worker.py:253-254,265-266,274-275)
+  SB_C_VALID, SB_S_VALID, SB_D_VALID,       // 1.0 once the normaliser is frozen
+  SB_C_COEF, SB_S_COEF, SB_D_COEF,          // multipliers used by the combine kernel
+  SB_C_LOSS, SB_C_GRAD, SB_S_LOSS, SB_S_GRAD, SB_D_LOSS, SB_D_GRAD,   // trace values
+  SB_S_DSCALE,        // power-of-two scale applied to the fp16 copy of D
+  ST2_SCAL_PER_BLOB_USED
+};
+static_assert(ST2_SCAL_PER_BLOB_USED <= ST2_SCAL_PER_BLOB, "scalar block too small");
+
+struct st2_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = 0;
+  std::string err;
+  // master fp32 weights (device): OIHW + bias, per conv
+  float* w_oihw[ST2_NUM_CONVS] = {};
+  float* bias[ST2_NUM_CONVS] = {};
+  int cin[ST2_NUM_CONVS] = {};
+  int cout[ST2_NUM_CONVS] = {};
+  // exact-mode packs: forward [tap][ci][co], backward-data [tap'][co][ci]
+  float* wf32_fwd[ST2_NUM_CONVS] = {};
+  float* wf32_bwd[ST2_NUM_CONVS] = {};
+  // tensor-core packs (fp16, K-major): forward [co][tap][ci], backward [ci][tap'][co]
+  __half* wh_fwd[ST2_NUM_CONVS] = {};
+  __half* wh_bwd[ST2_NUM_CONVS] = {};
+  void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled entry point
+  long long launches = 0;          // kernels launched through this context
+  // optional per-category device timing (CUDA events on the launch stream), see st2_profile()
+  bool prof_on = false;
+  struct ProfSpan { int cat; cudaEvent_t a, b; };
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+};
+
+// RAII span: records an event pair around the launches issued in its scope when profiling is on
+struct ProfScope {
+  st2_ctx* ctx; int idx;
+  ProfScope(st2_ctx* c, int cat);
+  ~ProfScope();
+};
+
+int st2_fail(st2_ctx* ctx, int code, const char* fmt, ...);
+
+#define ST2_CUDA(ctx, expr)                                                             \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return st2_fail((ctx), ST2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define ST2_LAUNCH_CHECK(ctx)                                                           \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess)                                                              \
+      return st2_fail((ctx), ST2_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+// ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of up to NV per-thread fp32 partials; one double atomicAdd per value per block.
+template <int NV>
+__device__ __forceinline__ void block_accumulate(const float (&v)[NV], double* const (&dst)[NV]) {
+  __shared__ double sh[NV][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double w = warp_sum_d((double)v[i]);
+    if (lane == 0) sh[i][warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double w = lane < nwarps ? sh[i][lane] : 0.0;
+      w = warp_sum_d(w);
+      if (lane == 0 && dst[i] != nullptr) atomicAdd(dst[i], w);
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int pool_extent(int n) { return n > 1 ? (n - 2 + 1) / 2 + 1 : 1; }   // ceil((n-2)/2)+1

@@ -1,0 +1,319 @@
+// tcgen05 implicit-GEMM 3x3 / 1x1 convolution on fp16 NHWC activations (K1, K2, K6 of SURVEY 2.4).
+//
+//   out[p, n] = epi( sum_{tap, c} in[p + off(tap), c] * w[n, tap, c] )        M = pixels, N = cout, K = taps*cin
+//
+// * A operand: for every (tap, 64-channel block) one TMA *tiled* 3-D box {64 ch, TW, TH} of the NHWC
+//   tensor at pixel offset (h0 + dh, w0 + dw).  Out-of-bounds rows/columns are zero-filled by the
+//   TMA unit, which IS the pad-1 border; the box lands in shared memory as a 128-row x 128-byte
+//   K-major SWIZZLE_128B tile, exactly the UMMA canonical layout -- no im2col buffer exists anywhere.
+// * B operand: packed weights [n][tap][c] (K-major), 2-D box {64, BN}.
+// * MMA: tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16 per instruction, fp32 accumulators in
+//   TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop of i+1.
+// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+//   (tcgen05.ld 32x32b -> bias/ReLU | ReLU-mask | raw -> fp16 -> 64-byte vector stores).
+// * Persistent: grid = min(tiles, SMs); static round-robin tile order with the cout block fastest
+//   so CTAs working on the same pixels at the same time share the A tile through L2.
+// The same kernel runs forward (weights [co][tap][ci]), data-gradient (weights [ci][tap'][co],
+// taps flipped) and the style-gradient 1x1 contraction (weights = scaled Gram difference).
+#include "st2_kernels.h"
+#include "st2_tc.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // pixels per tile
+constexpr int BK = 64;           // fp16 elements per K block = 128 bytes = one swizzle row
+constexpr int kNumThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BN> struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;                 // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct ConvGeom {
+  int H, W, cin, cout, taps;
+  int TH, TW, tiles_h, tiles_w, n_blocks, total_tiles, k_iters, cblocks;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
+               __half* __restrict__ out, const int epi, const float out_scale, double* sumsq) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by SWIZZLE_128B operand tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;                         // [kStages]
+  uint64_t* empty_bar = bars + C::kStages;           // [kStages]
+  uint64_t* tmem_full = bars + 2 * C::kStages;       // [2]
+  uint64_t* tmem_empty = bars + 2 * C::kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 128); }
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, C::kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int nb = tile % g.n_blocks, pt = tile / g.n_blocks;
+        const int h0 = (pt / g.tiles_w) * g.TH, w0 = (pt % g.tiles_w) * g.TW;
+        for (int it = 0; it < g.k_iters; ++it) {
+          const int tap = it / g.cblocks, cb = it - tap * g.cblocks;
+          const int dh = (g.taps == 9) ? tap / 3 - 1 : 0;
+          const int dw = (g.taps == 9) ? tap % 3 - 1 : 0;
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          tc::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tc::tma_load_3d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], cb * BK, w0 + dw, h0 + dh);
+          tc::tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], tap * g.cin + cb * BK, nb * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_f16(BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < g.k_iters; ++it) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint64_t a_desc = tc::smem_desc_k_sw128(tc::smem_u32(smem_a + stage * C::kABytes));
+          const uint64_t b_desc = tc::smem_desc_k_sw128(tc::smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)            // +32 bytes (>>4 = 2) per 16-element K step
+            tc::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
+          tc::umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ epilogue ====================================
+    const int ew = warp - kEpiWarp0;                   // == warp % 4: TMEM lane quarter of this warp
+    const int row = ew * 32 + lane;                    // pixel index inside the tile
+    float ss = 0.f;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int nb = tile % g.n_blocks, pt = tile / g.n_blocks;
+      const int h = (pt / g.tiles_w) * g.TH + row / g.TW;
+      const int w = (pt % g.tiles_w) * g.TW + row % g.TW;
+      const bool valid = (h < g.H) && (w < g.W);
+      const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      tc::mbar_wait(&tmem_full[acc], acc_phase);
+      tc::fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(t_row + c * 32, r);
+        tc::tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (epi == EPI_BIAS_RELU) {
+            const float4* bp = reinterpret_cast<const float4*>(bias + nb * BN + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = __ldg(bp + q);
+              v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x, 0.f);
+              v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y, 0.f);
+              v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z, 0.f);
+              v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w, 0.f);
+            }
+          } else if (epi == EPI_MASK) {
+            const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 a = __ldg(ap + q);
+              const __half2* hp = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(hp[e]);
+                if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
+                if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= out_scale;
+            if (sumsq != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(out + obase + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            __half2* hp = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hp[e] = __floats2half2_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            op[q] = o;
+          }
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&tmem_empty[acc]);
+    }
+    if (sumsq != nullptr) {
+      const double tot = warp_sum_d((double)ss);
+      if (lane == 0) atomicAdd(sumsq, tot);
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct TcConvPlan {
+  CUtensorMap tmap_a, tmap_b;
+  ConvGeom g;
+  int bn;
+};
+
+static int get_encoder(st2_ctx* ctx, EncodeTiledFn* fn) {
+  if (!ctx->tmap_encode) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ST2_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess)
+      return st2_fail(ctx, ST2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    ctx->tmap_encode = p;
+  }
+  *fn = reinterpret_cast<EncodeTiledFn>(ctx->tmap_encode);
+  return 0;
+}
+
+int st2_encode_tmap(st2_ctx* ctx, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn enc;
+  int rc = get_encoder(ctx, &enc);
+  if (rc) return rc;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return st2_fail(ctx, ST2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, int H, int W, int cin, int cout,
+                        int taps, TcConvPlan** out) {
+  if (cin % 64 || cout % 64 || (taps != 9 && taps != 1))
+    return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: cin/cout must be multiples of 64 (got %d/%d)", cin, cout);
+  TcConvPlan* p = new TcConvPlan();
+  ConvGeom& g = p->g;
+  g.H = H; g.W = W; g.cin = cin; g.cout = cout; g.taps = taps;
+  g.TW = (W <= 4) ? 4 : (W <= 8 ? 8 : 16);
+  g.TH = BM / g.TW;
+  g.tiles_h = (H + g.TH - 1) / g.TH;
+  g.tiles_w = (W + g.TW - 1) / g.TW;
+  p->bn = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  g.n_blocks = cout / p->bn;
+  g.total_tiles = g.tiles_h * g.tiles_w * g.n_blocks;
+  g.cblocks = cin / BK;
+  g.k_iters = taps * g.cblocks;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH};
+    int rc = st2_encode_tmap(ctx, &p->tmap_a, in, 3, dims, strides, box);
+    if (rc) { delete p; return rc; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout};
+    cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p->bn};
+    int rc = st2_encode_tmap(ctx, &p->tmap_b, w_packed, 2, dims, strides, box);
+    if (rc) { delete p; return rc; }
+  }
+  *out = p;
+  return 0;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
+
+template <int BN>
+static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
+                     float out_scale, double* sumsq) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = p->g.total_tiles < ctx->sm_count ? p->g.total_tiles : ctx->sm_count;
+  tc_conv_kernel<BN><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias,
+                                                                              act, out, epi, out_scale, sumsq);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
+                   float out_scale, double* sumsq) {
+  if (epi == EPI_BIAS_RELU && !bias) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: bias required");
+  if (epi == EPI_MASK && !act) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: act required");
+  switch (p->bn) {
+    case 256: return launch_bn<256>(ctx, p, bias, act, out, epi, out_scale, sumsq);
+    case 128: return launch_bn<128>(ctx, p, bias, act, out, epi, out_scale, sumsq);
+    default:  return launch_bn<64>(ctx, p, bias, act, out, epi, out_scale, sumsq);
+  }
+}
+
+// ---- tcgen05 Gram (st2_gram_tc.cu provides the real one once enabled) --------------------------
+#ifndef ST2_HAVE_TC_GRAM
+struct TcGramPlan { int unused; };
+int tc_gram_plan_create(st2_ctx* ctx, const __half*, int, long long, TcGramPlan**) {
+  return st2_fail(ctx, ST2_ERR_UNSUPPORTED, "tcgen05 Gram not built");
+}
+void tc_gram_plan_destroy(TcGramPlan* p) { delete p; }
+int tc_gram_launch(st2_ctx* ctx, TcGramPlan*, double*) {
+  return st2_fail(ctx, ST2_ERR_UNSUPPORTED, "tcgen05 Gram not built");
+}
+#endif

@@ -1,0 +1,72 @@
+// Internal launch wrappers shared between translation units of libst2.
+#pragma once
+#include "st2_common.cuh"
+
+// epilogue modes of the convolution kernels
+enum { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_RAW = 2 };
+
+// ---- st2_layers.cu (layout-agnostic / CUDA-core kernels) ------------------------------------
+// first layer: x fp32 NCHW (3 planes) -> NHWC T (64 ch), bias + ReLU     (K1, conv1_1)
+template <typename T>
+int launch_conv_first_fwd(st2_ctx* ctx, const float* x, const float* w_fwd /*[27][64]*/, const float* bias,
+                          T* out, int H, int W);
+// first layer data gradient: g NHWC T (64 ch) -> fp32 NCHW (3 planes)    (K2, conv1_1)
+template <typename T>
+int launch_conv_first_bwd(st2_ctx* ctx, const T* g, const float* w_bwd /*[9][64][3] flipped*/, float* gx,
+                          int H, int W);
+// exact fp32 3x3 conv on NHWC float; w = [tap][cin][cout]; epi per EPI_*; act used by EPI_MASK
+int launch_conv_exact(st2_ctx* ctx, const float* in, const float* w, const float* bias, const float* act,
+                      float* out, int H, int W, int cin, int cout, int epi);
+template <typename T>
+int launch_pool_fwd(st2_ctx* ctx, const T* in, T* out, int C, int H, int W);
+// route g_pool back to the window's first maximum of `act`; apply_mask multiplies by act > 0
+template <typename T>
+int launch_pool_bwd(st2_ctx* ctx, const T* act, const T* g_pool, T* g_out, int C, int H, int W,
+                    int apply_mask);
+// out = mask(gin) + cc (F - Fc) + sc S + dc F ; coefficients read from scal (device doubles) or host
+struct CombineArgs {
+  const void* gin;      // nullable
+  const void* act;      // F (always given)
+  const void* fc;       // nullable
+  const void* sraw;     // nullable
+  void* out;
+  long long n;
+  int apply_mask;
+  const double* coef;   // device: coef[0]=cc coef[1]=sc coef[2]=dc (nullable -> host values below)
+  float h_cc, h_sc, h_dc;
+};
+template <typename T> int launch_combine(st2_ctx* ctx, const CombineArgs& a);
+// sums[0] += sum (F-Fc)^2 (if fc), sums[1] += sum F^2
+template <typename T>
+int launch_feature_sums(st2_ctx* ctx, const T* act, const T* fc, long long n, double* sum_diff_sq,
+                        double* sum_sq);
+// Gd (C*C doubles, pre-zeroed) += sum_p F[p,i] F[p,j]; strides in elements
+template <typename T>
+int launch_gram_generic(st2_ctx* ctx, const T* F, int C, long long HW, long long sp, long long sc, double* Gd);
+// D = Gd/(C*HW) - A (A nullable -> D = G); out_f32 = D ; *sum_dsq += sum D^2
+int launch_gram_finalize(st2_ctx* ctx, const double* Gd, const float* A, float* D, int C, long long HW,
+                         double* sum_dsq);
+// raw[p,i] = sum_j D[i,j] F[p,j]  (strided, any T); *sum_rawsq += sum raw^2
+template <typename T>
+int launch_style_grad_generic(st2_ctx* ctx, const T* F, const float* D, T* raw, int C, long long HW,
+                              long long sp, long long sc, double* sum_rawsq);
+template <typename T>
+int launch_export_nchw(st2_ctx* ctx, const T* nhwc, float* nchw, int C, int H, int W);
+template <typename T>
+int launch_import_nchw(st2_ctx* ctx, const float* nchw, T* nhwc, int C, int H, int W);
+int launch_add_inplace(st2_ctx* ctx, float* y, const float* x, float coef_host, const double* coef_dev,
+                       long long n);
+
+// ---- st2_conv_tc.cu (tcgen05 implicit GEMM, fp16 NHWC) -----------------------------------------
+struct TcConvPlan;     // tensor maps + tile geometry for one (layer, direction, canvas)
+int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, int H, int W, int cin,
+                        int cout, int taps, TcConvPlan** out);
+void tc_conv_plan_destroy(TcConvPlan* p);
+// epi per EPI_*; bias fp32 (EPI_BIAS_RELU); act fp16 NHWC (EPI_MASK); sumsq nullable (sum of fp32 outputs^2)
+int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
+                   float out_scale, double* sumsq);
+// Gram partials with tcgen05 (MN-major operands): Gd += F^T F for fp16 NHWC features
+struct TcGramPlan;
+int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGramPlan** out);
+void tc_gram_plan_destroy(TcGramPlan* p);
+int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, double* Gd);

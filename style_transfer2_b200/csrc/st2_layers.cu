@@ -1,0 +1,565 @@
+// CUDA-core kernels of the hot path: first/last-layer convolutions, the exact fp32 convolution
+// used by ST2_PREC_FP32, ceil-mode max-pool and its backward, the loss "combine" pass, feature
+// reductions, the strided Gram / style-gradient contractions and layout conversions.
+// Reference semantics: worker.py:77-106 (model seam), 231-301 (objective); Caffe layers [ext].
+#include "st2_kernels.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int ew_grid(long long work_items, int sm_count) {
+  long long blocks = (work_items + kThreads - 1) / kThreads;
+  long long cap = (long long)sm_count * 16;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+// =============================================================================== conv1_1 forward
+// One block: 64 consecutive pixels of one row x 64 output channels.  Thread = (pixel, 16 couts).
+template <typename T>
+__global__ void conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                      const float* __restrict__ bias, T* __restrict__ out, int H, int W) {
+  __shared__ float sw[27 * 64];
+  __shared__ float sb[64];
+  __shared__ float sx[3][3][66];
+  const int tiles_w = (W + 63) / 64;
+  const int h = blockIdx.x / tiles_w;
+  const int w0 = (blockIdx.x % tiles_w) * 64;
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * 3 * 66; i += blockDim.x) {
+    const int c = i / (3 * 66), r = (i / 66) % 3, col = i % 66;
+    const int hh = h + r - 1, ww = w0 + col - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((long long)c * H + hh) * W + ww];
+    sx[c][r][col] = v;
+  }
+  __syncthreads();
+  const int px = threadIdx.x & 63, cg = threadIdx.x >> 6;
+  const int ww = w0 + px;
+  if (ww >= W) return;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = sb[cg * 16 + j];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float v = sx[c][r][px + s];
+        const float* wr = &sw[((r * 3 + s) * 3 + c) * 64 + cg * 16];     // [tap][ci][co]
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+      }
+  T* o = out + ((long long)h * W + ww) * 64 + cg * 16;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = from_f<T>(fmaxf(acc[j], 0.f));
+}
+
+// =============================================================================== conv1_1 dgrad
+// gx[ci][h][w] = sum_{tap,co} g[h+1-r][w+1-s][co] * W[co][ci][r][s];  w_bwd = [tap'][co][ci] with
+// tap' already flipped so the kernel reads g at (h + r' - 1, w + s' - 1).
+template <typename T>
+__global__ void conv_first_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w,
+                                      float* __restrict__ gx, int H, int W) {
+  __shared__ float sw[9 * 64 * 3];
+  for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)H * W) return;
+  const int h = (int)(p / W), ww = (int)(p % W);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int r = 0; r < 3; ++r) {
+    const int hh = h + r - 1;
+    if (hh < 0 || hh >= H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int wc = ww + s - 1;
+      if (wc < 0 || wc >= W) continue;
+      const T* gp = g + ((long long)hh * W + wc) * 64;
+      const float* wr = &sw[(r * 3 + s) * 64 * 3];
+#pragma unroll 8
+      for (int co = 0; co < 64; ++co) {
+        const float v = to_f<T>(gp[co]);
+        a0 = fmaf(v, wr[co * 3 + 0], a0);
+        a1 = fmaf(v, wr[co * 3 + 1], a1);
+        a2 = fmaf(v, wr[co * 3 + 2], a2);
+      }
+    }
+  }
+  const long long HW = (long long)H * W;
+  gx[p] = a0;
+  gx[HW + p] = a1;
+  gx[2 * HW + p] = a2;
+}
+
+// =============================================================================== exact fp32 conv
+// Implicit GEMM on CUDA cores: block tile = 8x8 pixels x 64 couts, K step = 16 input channels of
+// one tap, 4x4 register micro-tile per thread.
+template <int EPI>
+__global__ void __launch_bounds__(256)
+conv_exact_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                  const float* __restrict__ act, float* __restrict__ out, int H, int W, int cin, int cout) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64];
+  const int tiles_w = (W + 7) / 8;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
+  const int h0 = th * 8, w0 = tw * 8;
+  const int co0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  // A loader: pixel lp, 4 consecutive input channels
+  const int lp = t & 63, lk = (t >> 6) * 4;
+  const int lph = h0 + (lp >> 3), lpw = w0 + (lp & 7);
+  // B loader
+  const int bk = t >> 4, bc = (t & 15) * 4;
+  float acc[4][4] = {};
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = lph + tap / 3 - 1, wc = lpw + tap % 3 - 1;
+    const bool inb = hh >= 0 && hh < H && wc >= 0 && wc < W;
+    const float* ip = in + ((long long)hh * W + wc) * cin;
+    const float* wp = w + (long long)tap * cin * cout;
+    for (int c0 = 0; c0 < cin; c0 += 16) {
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inb) av = *reinterpret_cast<const float4*>(ip + c0 + lk);
+      const float4 bv = *reinterpret_cast<const float4*>(wp + (long long)(c0 + bk) * cout + co0 + bc);
+      __syncthreads();
+      As[lk + 0][lp] = av.x; As[lk + 1][lp] = av.y; As[lk + 2][lp] = av.z; As[lk + 3][lp] = av.w;
+      *reinterpret_cast<float4*>(&Bs[bk][bc]) = bv;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float aa[4] = {a.x, a.y, a.z, a.w};
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pl = ty * 4 + i;
+    const int h = h0 + (pl >> 3), ww = w0 + (pl & 7);
+    if (h >= H || ww >= W) continue;
+    const long long o = ((long long)h * W + ww) * cout + co0 + tx * 4;
+    float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (EPI == EPI_BIAS_RELU) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + co0 + tx * 4);
+      v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f);
+      v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+    } else if (EPI == EPI_MASK) {
+      const float4 a = *reinterpret_cast<const float4*>(act + o);
+      v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f;
+      v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+    }
+    *reinterpret_cast<float4*>(out + o) = v;
+  }
+}
+
+// =============================================================================== max-pool 2x2/2 ceil
+template <typename T>
+__global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int C, int H, int W, int Ho,
+                                int Wo) {
+  const long long total = (long long)Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long p = i / C;
+    const int wo = (int)(p % Wo), ho = (int)(p / Wo);
+    const int h = ho * 2, w = wo * 2;
+    float m = to_f<T>(in[((long long)h * W + w) * C + c]);
+    if (w + 1 < W) m = fmaxf(m, to_f<T>(in[((long long)h * W + w + 1) * C + c]));
+    if (h + 1 < H) {
+      m = fmaxf(m, to_f<T>(in[((long long)(h + 1) * W + w) * C + c]));
+      if (w + 1 < W) m = fmaxf(m, to_f<T>(in[((long long)(h + 1) * W + w + 1) * C + c]));
+    }
+    out[i] = from_f<T>(m);
+  }
+}
+
+// Caffe PoolingLayer backward: the whole diff of a window goes to its first maximum in (h, w) scan
+// order (strict '>' update) [ext]; optional ReLU mask of the layer below (act > 0).
+template <typename T>
+__global__ void pool_bwd_kernel(const T* __restrict__ act, const T* __restrict__ gp, T* __restrict__ gout,
+                                int C, int H, int W, int Ho, int Wo, int apply_mask) {
+  const long long total = (long long)Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long p = i / C;
+    const int wo = (int)(p % Wo), ho = (int)(p / Wo);
+    const int h = ho * 2, w = wo * 2;
+    const bool has_r = w + 1 < W, has_d = h + 1 < H;
+    const long long i00 = ((long long)h * W + w) * C + c;
+    const long long i01 = i00 + C, i10 = i00 + (long long)W * C, i11 = i10 + C;
+    float best = to_f<T>(act[i00]);
+    int arg = 0;
+    if (has_r) { const float v = to_f<T>(act[i01]); if (v > best) { best = v; arg = 1; } }
+    if (has_d) {
+      const float v = to_f<T>(act[i10]); if (v > best) { best = v; arg = 2; }
+      if (has_r) { const float v2 = to_f<T>(act[i11]); if (v2 > best) { best = v2; arg = 3; } }
+    }
+    float g = to_f<T>(gp[i]);
+    if (apply_mask && !(best > 0.f)) g = 0.f;
+    const T z = from_f<T>(0.f), gv = from_f<T>(g);
+    gout[i00] = arg == 0 ? gv : z;
+    if (has_r) gout[i01] = arg == 1 ? gv : z;
+    if (has_d) {
+      gout[i10] = arg == 2 ? gv : z;
+      if (has_r) gout[i11] = arg == 3 ? gv : z;
+    }
+  }
+}
+
+// =============================================================================== loss combine
+template <typename T>
+__global__ void combine_kernel(const T* __restrict__ gin, const T* __restrict__ act, const T* __restrict__ fc,
+                               const T* __restrict__ sraw, T* __restrict__ out, long long n, int apply_mask,
+                               const double* __restrict__ coef, float h_cc, float h_sc, float h_dc) {
+  float cc = h_cc, sc = h_sc, dc = h_dc;
+  if (coef != nullptr) { cc = (float)coef[0]; sc = (float)coef[1]; dc = (float)coef[2]; }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float f = to_f<T>(act[i]);
+    float v = 0.f;
+    if (gin != nullptr) {
+      v = to_f<T>(gin[i]);
+      if (apply_mask && !(f > 0.f)) v = 0.f;
+    }
+    if (fc != nullptr) v = fmaf(cc, f - to_f<T>(fc[i]), v);
+    if (sraw != nullptr) v = fmaf(sc, to_f<T>(sraw[i]), v);
+    if (dc != 0.f) v = fmaf(dc, f, v);
+    out[i] = from_f<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void feature_sums_kernel(const T* __restrict__ act, const T* __restrict__ fc, long long n,
+                                    double* sum_diff_sq, double* sum_sq) {
+  float a = 0.f, b = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float f = to_f<T>(act[i]);
+    b = fmaf(f, f, b);
+    if (fc != nullptr) { const float d = f - to_f<T>(fc[i]); a = fmaf(d, d, a); }
+  }
+  float v[2] = {a, b};
+  double* dst[2] = {fc != nullptr ? sum_diff_sq : nullptr, sum_sq};
+  block_accumulate<2>(v, dst);
+}
+
+// =============================================================================== strided Gram
+// Block = 64 x 64 tile of G over one chunk of pixels; thread micro-tile 4 x 4.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gram_generic_kernel(const T* __restrict__ F, int C, long long HW, long long sp, long long sc,
+                    double* __restrict__ Gd, long long chunk) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
+  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  const long long p_begin = (long long)blockIdx.z * chunk;
+  const long long p_end = min(HW, p_begin + chunk);
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  float acc[4][4] = {};
+  for (long long p0 = p_begin; p0 < p_end; p0 += 16) {
+    __syncthreads();
+    for (int e = t; e < 16 * 64; e += 256) {
+      const int ch = e & 63, pp = e >> 6;
+      const long long p = p0 + pp;
+      float a = 0.f, b = 0.f;
+      if (p < p_end) {
+        if (i0 + ch < C) a = to_f<T>(F[p * sp + (long long)(i0 + ch) * sc]);
+        if (j0 + ch < C) b = to_f<T>(F[p * sp + (long long)(j0 + ch) * sc]);
+      }
+      As[pp][ch] = a;
+      Bs[pp][ch] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float aa[4] = {a.x, a.y, a.z, a.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = i0 + ty * 4 + i, gj = j0 + tx * 4 + j;
+      if (gi < C && gj < C) atomicAdd(&Gd[(long long)gi * C + gj], (double)acc[i][j]);
+    }
+}
+
+__global__ void gram_finalize_kernel(const double* __restrict__ Gd, const float* __restrict__ A,
+                                     float* __restrict__ D, int C, long long HW, double* sum_dsq) {
+  const long long n = (long long)C * C;
+  const float denom = (float)((double)C * (double)HW);         // np.float32(x.size), worker.py:114
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float g = (float)Gd[i] / denom;
+    if (A != nullptr) g -= A[i];
+    D[i] = g;
+    acc = fmaf(g, g, acc);
+  }
+  float v[1] = {acc};
+  double* dst[1] = {sum_dsq};
+  block_accumulate<1>(v, dst);
+}
+
+// raw[p, i] = sum_j D[i, j] F[p, j]; block = 64 pixels x 64 channels i, K step 16 channels j
+template <typename T>
+__global__ void __launch_bounds__(256)
+style_grad_generic_kernel(const T* __restrict__ F, const float* __restrict__ D, T* __restrict__ raw, int C,
+                          long long HW, long long sp, long long sc, double* sum_rawsq) {
+  __shared__ __align__(16) float As[16][64 + 4];     // [j][pixel]
+  __shared__ __align__(16) float Bs[16][64 + 4];     // [j][i]
+  const long long p0 = (long long)blockIdx.x * 64;
+  const int i0 = blockIdx.y * 64;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  float acc[4][4] = {};
+  for (int j0 = 0; j0 < C; j0 += 16) {
+    __syncthreads();
+    for (int e = t; e < 16 * 64; e += 256) {
+      const int jj = e & 15, q = e >> 4;              // q: pixel (A) or channel i (B)
+      float a = 0.f, b = 0.f;
+      if (j0 + jj < C) {
+        if (p0 + q < HW) a = to_f<T>(F[(p0 + q) * sp + (long long)(j0 + jj) * sc]);
+        if (i0 + q < C) b = D[(long long)(i0 + q) * C + j0 + jj];
+      }
+      As[jj][q] = a;
+      Bs[jj][q] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float aa[4] = {a.x, a.y, a.z, a.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long p = p0 + ty * 4 + i;
+      const int ci = i0 + tx * 4 + j;
+      if (p < HW && ci < C) {
+        raw[p * sp + (long long)ci * sc] = from_f<T>(acc[i][j]);
+        ss = fmaf(acc[i][j], acc[i][j], ss);
+      }
+    }
+  float v[1] = {ss};
+  double* dst[1] = {sum_rawsq};
+  block_accumulate<1>(v, dst);
+}
+
+// =============================================================================== layout conversion
+template <typename T>
+__global__ void export_nchw_kernel(const T* __restrict__ nhwc, float* __restrict__ nchw, int C, long long HW) {
+  __shared__ float tile[32][33];
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long p = p0 + r;
+    const int c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? to_f<T>(nhwc[p * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const long long p = p0 + threadIdx.x;
+    if (p < HW && c < C) nchw[(long long)c * HW + p] = tile[threadIdx.x][r];
+  }
+}
+
+template <typename T>
+__global__ void import_nchw_kernel(const float* __restrict__ nchw, T* __restrict__ nhwc, int C, long long HW) {
+  __shared__ float tile[32][33];
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const long long p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? nchw[(long long)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long p = p0 + r;
+    const int c = c0 + threadIdx.x;
+    if (p < HW && c < C) nhwc[p * C + c] = from_f<T>(tile[threadIdx.x][r]);
+  }
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, float coef_host,
+                                   const double* coef_dev, long long n) {
+  const float c = coef_dev ? (float)coef_dev[0] : coef_host;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaf(c, x[i], y[i]);
+}
+
+}  // namespace
+
+// =============================================================================== launch wrappers
+template <typename T>
+int launch_conv_first_fwd(st2_ctx* ctx, const float* x, const float* w, const float* bias, T* out, int H,
+                          int W) {
+  const int blocks = H * ((W + 63) / 64);
+  conv_first_fwd_kernel<T><<<blocks, 256, 0, ctx->stream>>>(x, w, bias, out, H, W);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_conv_first_fwd<float>(st2_ctx*, const float*, const float*, const float*, float*, int, int);
+template int launch_conv_first_fwd<__half>(st2_ctx*, const float*, const float*, const float*, __half*, int, int);
+
+template <typename T>
+int launch_conv_first_bwd(st2_ctx* ctx, const T* g, const float* w, float* gx, int H, int W) {
+  const long long hw = (long long)H * W;
+  conv_first_bwd_kernel<T><<<cdiv(hw, 128), 128, 0, ctx->stream>>>(g, w, gx, H, W);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_conv_first_bwd<float>(st2_ctx*, const float*, const float*, float*, int, int);
+template int launch_conv_first_bwd<__half>(st2_ctx*, const __half*, const float*, float*, int, int);
+
+int launch_conv_exact(st2_ctx* ctx, const float* in, const float* w, const float* bias, const float* act,
+                      float* out, int H, int W, int cin, int cout, int epi) {
+  if (cin % 16 || cout % 64) return st2_fail(ctx, ST2_ERR_ARG, "conv_exact: cin %% 16 / cout %% 64");
+  dim3 grid(((H + 7) / 8) * ((W + 7) / 8), cout / 64);
+  if (epi == EPI_BIAS_RELU)
+    conv_exact_kernel<EPI_BIAS_RELU><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout);
+  else if (epi == EPI_MASK)
+    conv_exact_kernel<EPI_MASK><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout);
+  else
+    conv_exact_kernel<EPI_RAW><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+template <typename T>
+int launch_pool_fwd(st2_ctx* ctx, const T* in, T* out, int C, int H, int W) {
+  const int Ho = pool_extent(H), Wo = pool_extent(W);
+  pool_fwd_kernel<T><<<ew_grid((long long)Ho * Wo * C, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+      in, out, C, H, W, Ho, Wo);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_pool_fwd<float>(st2_ctx*, const float*, float*, int, int, int);
+template int launch_pool_fwd<__half>(st2_ctx*, const __half*, __half*, int, int, int);
+
+template <typename T>
+int launch_pool_bwd(st2_ctx* ctx, const T* act, const T* g_pool, T* g_out, int C, int H, int W, int apply_mask) {
+  const int Ho = pool_extent(H), Wo = pool_extent(W);
+  pool_bwd_kernel<T><<<ew_grid((long long)Ho * Wo * C, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+      act, g_pool, g_out, C, H, W, Ho, Wo, apply_mask);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_pool_bwd<float>(st2_ctx*, const float*, const float*, float*, int, int, int, int);
+template int launch_pool_bwd<__half>(st2_ctx*, const __half*, const __half*, __half*, int, int, int, int);
+
+template <typename T>
+int launch_combine(st2_ctx* ctx, const CombineArgs& a) {
+  combine_kernel<T><<<ew_grid(a.n, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+      (const T*)a.gin, (const T*)a.act, (const T*)a.fc, (const T*)a.sraw, (T*)a.out, a.n, a.apply_mask, a.coef,
+      a.h_cc, a.h_sc, a.h_dc);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_combine<float>(st2_ctx*, const CombineArgs&);
+template int launch_combine<__half>(st2_ctx*, const CombineArgs&);
+
+template <typename T>
+int launch_feature_sums(st2_ctx* ctx, const T* act, const T* fc, long long n, double* sum_diff_sq,
+                        double* sum_sq) {
+  feature_sums_kernel<T><<<ew_grid(n / 4 + 1, ctx->sm_count), kThreads, 0, ctx->stream>>>(act, fc, n, sum_diff_sq,
+                                                                                          sum_sq);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_feature_sums<float>(st2_ctx*, const float*, const float*, long long, double*, double*);
+template int launch_feature_sums<__half>(st2_ctx*, const __half*, const __half*, long long, double*, double*);
+
+template <typename T>
+int launch_gram_generic(st2_ctx* ctx, const T* F, int C, long long HW, long long sp, long long sc, double* Gd) {
+  const int tiles = (C + 63) / 64;
+  long long want_splits = ((long long)ctx->sm_count * 4) / ((long long)tiles * tiles);
+  if (want_splits < 1) want_splits = 1;
+  long long chunk = (HW + want_splits - 1) / want_splits;
+  if (chunk < 256) chunk = 256;
+  chunk = (chunk + 15) / 16 * 16;
+  const int splits = (int)((HW + chunk - 1) / chunk);
+  dim3 grid(tiles, tiles, splits);
+  gram_generic_kernel<T><<<grid, 256, 0, ctx->stream>>>(F, C, HW, sp, sc, Gd, chunk);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_gram_generic<float>(st2_ctx*, const float*, int, long long, long long, long long, double*);
+template int launch_gram_generic<__half>(st2_ctx*, const __half*, int, long long, long long, long long, double*);
+
+int launch_gram_finalize(st2_ctx* ctx, const double* Gd, const float* A, float* D, int C, long long HW,
+                         double* sum_dsq) {
+  gram_finalize_kernel<<<ew_grid((long long)C * C, ctx->sm_count), kThreads, 0, ctx->stream>>>(Gd, A, D, C, HW,
+                                                                                               sum_dsq);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+template <typename T>
+int launch_style_grad_generic(st2_ctx* ctx, const T* F, const float* D, T* raw, int C, long long HW,
+                              long long sp, long long sc, double* sum_rawsq) {
+  dim3 grid((unsigned)((HW + 63) / 64), (C + 63) / 64);
+  style_grad_generic_kernel<T><<<grid, 256, 0, ctx->stream>>>(F, D, raw, C, HW, sp, sc, sum_rawsq);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_style_grad_generic<float>(st2_ctx*, const float*, const float*, float*, int, long long,
+                                              long long, long long, double*);
+template int launch_style_grad_generic<__half>(st2_ctx*, const __half*, const float*, __half*, int, long long,
+                                               long long, long long, double*);
+
+template <typename T>
+int launch_export_nchw(st2_ctx* ctx, const T* nhwc, float* nchw, int C, int H, int W) {
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32), block(32, 8);
+  export_nchw_kernel<T><<<grid, block, 0, ctx->stream>>>(nhwc, nchw, C, HW);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_export_nchw<float>(st2_ctx*, const float*, float*, int, int, int);
+template int launch_export_nchw<__half>(st2_ctx*, const __half*, float*, int, int, int);
+
+template <typename T>
+int launch_import_nchw(st2_ctx* ctx, const float* nchw, T* nhwc, int C, int H, int W) {
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32), block(32, 8);
+  import_nchw_kernel<T><<<grid, block, 0, ctx->stream>>>(nchw, nhwc, C, HW);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template int launch_import_nchw<float>(st2_ctx*, const float*, float*, int, int, int);
+template int launch_import_nchw<__half>(st2_ctx*, const float*, __half*, int, int, int);
+
+int launch_add_inplace(st2_ctx* ctx, float* y, const float* x, float coef_host, const double* coef_dev,
+                       long long n) {
+  add_inplace_kernel<<<ew_grid(n, ctx->sm_count), kThreads, 0, ctx->stream>>>(y, x, coef_host, coef_dev, n);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}

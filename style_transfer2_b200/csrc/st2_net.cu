@@ -1,0 +1,738 @@
+// Context, weights, per-canvas plan and the orchestration of forward / backward / objective.
+// Reference: worker.py:32-106 (CaffeModel seam), 109-114 (gram_matrix), 231-301 (opfunc).
+#include "st2_kernels.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+// --------------------------------------------------------------------------------------------
+const BlobInfo g_blobs[ST2_NUM_BLOBS] = {
+    {"data", KIND_INPUT, 3, -1},
+    {"conv1_1", KIND_CONV, 64, 0},   {"conv1_2", KIND_CONV, 64, 1},   {"pool1", KIND_POOL, 64, -1},
+    {"conv2_1", KIND_CONV, 128, 2},  {"conv2_2", KIND_CONV, 128, 3},  {"pool2", KIND_POOL, 128, -1},
+    {"conv3_1", KIND_CONV, 256, 4},  {"conv3_2", KIND_CONV, 256, 5},  {"conv3_3", KIND_CONV, 256, 6},
+    {"conv3_4", KIND_CONV, 256, 7},  {"pool3", KIND_POOL, 256, -1},
+    {"conv4_1", KIND_CONV, 512, 8},  {"conv4_2", KIND_CONV, 512, 9},  {"conv4_3", KIND_CONV, 512, 10},
+    {"conv4_4", KIND_CONV, 512, 11}, {"pool4", KIND_POOL, 512, -1},
+    {"conv5_1", KIND_CONV, 512, 12}, {"conv5_2", KIND_CONV, 512, 13}, {"conv5_3", KIND_CONV, 512, 14},
+    {"conv5_4", KIND_CONV, 512, 15}, {"pool5", KIND_POOL, 512, -1},
+};
+
+static std::string g_create_error;
+
+int st2_fail(st2_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+static cudaEvent_t prof_event(st2_ctx* ctx) {
+  cudaEvent_t e = nullptr;
+  if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(st2_ctx* c, int cat) : ctx(c), idx(-1) {
+  if (!c || !c->prof_on) return;
+  st2_ctx::ProfSpan sp;
+  sp.cat = cat; sp.a = prof_event(c); sp.b = nullptr;
+  cudaEventRecord(sp.a, c->stream);
+  idx = (int)c->prof_spans.size();
+  c->prof_spans.push_back(sp);
+}
+
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  cudaEvent_t e = prof_event(ctx);
+  cudaEventRecord(e, ctx->stream);
+  ctx->prof_spans[idx].b = e;
+}
+
+// --------------------------------------------------------------------------------------------
+namespace {
+
+// dst index helpers for the four weight packs; src is OIHW (cout, cin, 3, 3)
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, float* f_fwd, float* f_bwd,
+                                    __half* h_fwd, __half* h_bwd) {
+  const long long total = (long long)cout * cin * 9;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i % 3), r = (int)((i / 3) % 3);
+    const int ci = (int)((i / 9) % cin), co = (int)(i / (9LL * cin));
+    const float v = w[i];
+    const int tap = r * 3 + s, tapf = (2 - r) * 3 + (2 - s);
+    f_fwd[((long long)tap * cin + ci) * cout + co] = v;              // [tap][ci][co]
+    f_bwd[((long long)tapf * cout + co) * cin + ci] = v;             // [tap'][co][ci]
+    if (h_fwd) h_fwd[((long long)co * 9 + tap) * cin + ci] = __float2half_rn(v);     // [co][tap][ci]
+    if (h_bwd) h_bwd[((long long)ci * 9 + tapf) * cout + co] = __float2half_rn(v);   // [ci][tap'][co]
+  }
+}
+
+struct EvalSpec {
+  int n;
+  int order[ST2_NUM_BLOBS];
+  float cw[ST2_NUM_BLOBS], sw[ST2_NUM_BLOBS], dw[ST2_NUM_BLOBS];
+  int C[ST2_NUM_BLOBS];
+  double nelem[ST2_NUM_BLOBS];
+  float tv, tv_power, p, p_power;
+  double N;
+};
+
+__device__ __forceinline__ bool w_on(float w) { return fabsf(w) > 1e-15f; }   // NaN -> false (worker.py:234)
+
+// zero the per-evaluation accumulators, keep norms / valid flags
+__global__ void clear_volatile_kernel(double* scal) {
+  for (int i = threadIdx.x; i < ST2_SCAL_TOTAL; i += blockDim.x) {
+    if (i >= ST2_SCAL_GLOBAL_BASE) { scal[i] = 0.0; continue; }
+    const int f = i % ST2_SCAL_PER_BLOB;
+    if (f < SB_C_NORM || f > SB_D_VALID) scal[i] = 0.0;
+  }
+}
+
+// fp16 copy of D scaled by a power of two chosen from rms(D): |D'| <= ~1, |D' F| <= ~max|F|
+__global__ void style_scale_kernel(const float* __restrict__ D, __half* __restrict__ Dh, int C, double* sb) {
+  const double n = (double)C * C;
+  const double rms = sqrt(sb[SB_S_GRAMSQ] / n);
+  float ds = 1.0f;
+  if (rms > 0.0 && isfinite(rms)) ds = exp2f(-ceilf(log2f((float)rms * (float)C)));
+  if (blockIdx.x == 0 && threadIdx.x == 0) sb[SB_S_DSCALE] = (double)ds;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)C * C;
+       i += (long long)gridDim.x * blockDim.x)
+    Dh[i] = __float2half_rn(D[i] * ds);
+}
+
+// worker.py:249-277: freeze normalisers on first use, derive combine coefficients and trace values
+__global__ void coef_kernel(EvalSpec es, double* scal) {
+  const int k = threadIdx.x;
+  if (k >= es.n) return;
+  const int b = es.order[k];
+  double* sb = scal + b * ST2_SCAL_PER_BLOB;
+  const double n = es.nelem[b];
+  const double C = (double)es.C[b];
+  if (w_on(es.cw[b])) {
+    const double msd = sb[SB_C_SUMSQ] / n;
+    if (sb[SB_C_VALID] == 0.0) { sb[SB_C_NORM] = (2.0 / n) * sqrt(msd); sb[SB_C_VALID] = 1.0; }
+    const double cn = sb[SB_C_NORM];
+    sb[SB_C_COEF] = (double)es.cw[b] / cn * (2.0 / n);
+    sb[SB_C_LOSS] = (double)es.cw[b] * msd / cn;
+    sb[SB_C_GRAD] = fabs((double)es.cw[b] / cn) * (2.0 / n) * sqrt(msd);
+  }
+  if (w_on(es.sw[b])) {
+    double ds = sb[SB_S_DSCALE];
+    if (ds == 0.0) ds = 1.0;
+    const double kk = 2.0 / (C * C * n);                       // 2 / (gram_diff.size * feat.size)
+    const double raw2 = sb[SB_S_RAWSQ] / (ds * ds);
+    if (sb[SB_S_VALID] == 0.0) { sb[SB_S_NORM] = kk * sqrt(raw2 / n); sb[SB_S_VALID] = 1.0; }
+    const double sn = sb[SB_S_NORM];
+    sb[SB_S_COEF] = (double)es.sw[b] / sn * kk / ds;
+    sb[SB_S_LOSS] = (double)es.sw[b] * (sb[SB_S_GRAMSQ] / (C * C)) / sn;
+    sb[SB_S_GRAD] = fabs((double)es.sw[b] / sn) * kk * sqrt(raw2 / n);
+  }
+  if (w_on(es.dw[b])) {
+    const double msf = sb[SB_D_SUMSQ] / n;
+    if (sb[SB_D_VALID] == 0.0) { sb[SB_D_NORM] = (2.0 / n) * sqrt(msf); sb[SB_D_VALID] = 1.0; }
+    const double dn = sb[SB_D_NORM];
+    sb[SB_D_COEF] = (double)es.dw[b] / dn * (-2.0 / n);
+    sb[SB_D_LOSS] = -(double)es.dw[b] * msf / dn;
+    sb[SB_D_GRAD] = fabs((double)es.dw[b] / dn) * (2.0 / n) * sqrt(msf);
+  }
+}
+
+// worker.py:279-301: totals in the reference's accumulation order
+__global__ void final_kernel(EvalSpec es, double* scal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* g = scal + ST2_SCAL_GLOBAL_BASE;
+  double scd = 0.0;
+  for (int k = 0; k < es.n; ++k) {
+    const int b = es.order[k];
+    const double* sb = scal + b * ST2_SCAL_PER_BLOB;
+    if (w_on(es.cw[b])) scd += sb[SB_C_LOSS];
+    if (w_on(es.sw[b])) scd += sb[SB_S_LOSS];
+    if (w_on(es.dw[b])) scd += sb[SB_D_LOSS];
+  }
+  g[ST2_G_SCD_LOSS] = scd;
+  g[ST2_G_T_LOSS] = (double)es.tv * g[ST2_G_TV_NORM];
+  g[ST2_G_P_LOSS] = (double)es.p * (g[ST2_G_P_NORM] / (double)es.p_power);
+  g[ST2_G_LOSS] = scd + g[ST2_G_T_LOSS] + g[ST2_G_P_LOSS];
+  g[ST2_G_SCD_GRAD] = sqrt(g[ST2_G_SCD_GRAD_SQ] / es.N);
+  g[ST2_G_T_GRAD] = sqrt(g[ST2_G_T_GRAD_SQ] / es.N);
+  g[ST2_G_P_GRAD] = sqrt(g[ST2_G_P_GRAD_SQ] / es.N);
+  g[ST2_G_GRAD] = sqrt(g[ST2_G_GRAD_SQ] / es.N);
+}
+
+struct Blob {
+  int C = 0, H = 0, W = 0;
+  void* act = nullptr;        // T NHWC (data: caller's fp32 NCHW x)
+  void* grad = nullptr;       // T NHWC gradient w.r.t. the (post-ReLU) blob
+  void* fc = nullptr;         // content target, same layout as act
+  void* sraw = nullptr;       // unscaled style gradient D F
+  void* inj = nullptr;        // imported diff for the model-seam backward
+  float* gram_target = nullptr;   // A, C x C fp32
+  float* D = nullptr;             // gram(F) - A, C x C fp32
+  __half* Dh = nullptr;           // scaled fp16 copy for the tcgen05 1x1 contraction
+  float cw = 0.f, sw = 0.f, dw = 0.f;
+  TcConvPlan* tc_fwd = nullptr;   // producing this blob (conv blobs, idx >= 1)
+  TcConvPlan* tc_bwd = nullptr;   // consuming grad of this blob, producing grad of the blob below
+  TcConvPlan* tc_style = nullptr;
+  TcGramPlan* tc_gram = nullptr;
+  long long n() const { return (long long)C * H * W; }
+};
+
+struct Inject {
+  bool on = false;
+  const void* fc = nullptr;
+  const void* sraw = nullptr;
+  const double* coef = nullptr;
+  float hcc = 0.f, hsc = 0.f, hdc = 0.f;
+};
+
+}  // namespace
+
+struct st2_plan {
+  st2_ctx* ctx;
+  int H, W, prec;
+  size_t esz;
+  Blob b[ST2_NUM_BLOBS];
+  double* scal = nullptr;
+  double* gram_acc = nullptr;     // 512 x 512 doubles
+  float* bwd = nullptr;           // d(scd)/d(data), fp32 NCHW
+  float* data_sraw = nullptr;
+  int order_n = 0;
+  int order[ST2_NUM_BLOBS];
+  float tv = 1.f, tv_power = 1.f, p = 1.f, p_power = 1.f;
+  const float* x_cur = nullptr;
+  int top_cur = -1;
+};
+
+static inline bool host_w_on(float w) { return fabsf(w) > 1e-15f; }
+
+template <typename T>
+static int forward_impl(st2_plan* pl, const float* x, int top) {
+  st2_ctx* ctx = pl->ctx;
+  pl->b[0].act = const_cast<float*>(x);
+  for (int i = 1; i <= top; ++i) {
+    Blob& cur = pl->b[i];
+    Blob& below = pl->b[i - 1];
+    int rc = 0;
+    const int fcat = g_blobs[i].kind != KIND_CONV ? 2 : (g_blobs[i].conv_index == 0 ? 1 : (pl->prec == ST2_PREC_FP32 ? 8 : 0));
+    ProfScope ps(ctx, fcat);
+    if (g_blobs[i].kind == KIND_CONV) {
+      const int ci = g_blobs[i].conv_index;
+      if (!ctx->w_oihw[ci]) return st2_fail(ctx, ST2_ERR_STATE, "weights of %s not loaded", g_blobs[i].name);
+      if (ci == 0) {
+        rc = launch_conv_first_fwd<T>(ctx, x, ctx->wf32_fwd[0], ctx->bias[0], (T*)cur.act, cur.H, cur.W);
+      } else if (pl->prec == ST2_PREC_FP32) {
+        rc = launch_conv_exact(ctx, (const float*)below.act, ctx->wf32_fwd[ci], ctx->bias[ci], nullptr,
+                               (float*)cur.act, cur.H, cur.W, below.C, cur.C, EPI_BIAS_RELU);
+      } else {
+        rc = tc_conv_launch(ctx, cur.tc_fwd, ctx->bias[ci], nullptr, (__half*)cur.act, EPI_BIAS_RELU, 1.f, nullptr);
+      }
+    } else {
+      rc = launch_pool_fwd<T>(ctx, (const T*)below.act, (T*)cur.act, below.C, below.H, below.W);
+    }
+    if (rc) return rc;
+  }
+  pl->x_cur = x;
+  pl->top_cur = top;
+  return 0;
+}
+
+// Gradient of sum_b <inj_b, blob_b> w.r.t. data with the reference's segment semantics
+// (worker.py:88-106): gradient from above passes through reluX_Y (mask), the injected diff does not.
+template <typename T>
+static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_out) {
+  st2_ctx* ctx = pl->ctx;
+  if (top > pl->top_cur) return st2_fail(ctx, ST2_ERR_STATE, "backward above the last forward's top blob");
+  if (top == 0) {
+    ST2_CUDA(ctx, cudaMemsetAsync(grad_out, 0, sizeof(float) * pl->b[0].n(), ctx->stream));
+  }
+  for (int i = top; i >= 1; --i) {
+    Blob& cur = pl->b[i];
+    Blob& below = pl->b[i - 1];
+    const bool have_above = (i < top);
+    const bool is_conv = g_blobs[i].kind == KIND_CONV;
+    int rc = 0;
+    if (inj[i].on) {
+      CombineArgs a;
+      a.gin = have_above ? cur.grad : nullptr;
+      a.act = cur.act; a.fc = inj[i].fc; a.sraw = inj[i].sraw; a.out = cur.grad; a.n = cur.n();
+      a.apply_mask = is_conv ? 1 : 0;
+      a.coef = inj[i].coef; a.h_cc = inj[i].hcc; a.h_sc = inj[i].hsc; a.h_dc = inj[i].hdc;
+      ProfScope ps(ctx, 5);
+      rc = launch_combine<T>(ctx, a);
+      if (rc) return rc;
+    } else if (!have_above) {
+      return st2_fail(ctx, ST2_ERR_STATE, "top blob carries no diff");
+    }
+    // does the producer of grad(below) apply below's ReLU mask itself?
+    const bool below_conv = g_blobs[i - 1].kind == KIND_CONV;
+    const int mask_below = (below_conv && !inj[i - 1].on) ? 1 : 0;
+    const int bcat = !is_conv ? 2 : (g_blobs[i].conv_index == 0 ? 1 : (pl->prec == ST2_PREC_FP32 ? 8 : 0));
+    ProfScope ps(ctx, bcat);
+    if (is_conv) {
+      const int ci = g_blobs[i].conv_index;
+      if (ci == 0) {
+        rc = launch_conv_first_bwd<T>(ctx, (const T*)cur.grad, ctx->wf32_bwd[0], grad_out, cur.H, cur.W);
+      } else if (pl->prec == ST2_PREC_FP32) {
+        rc = launch_conv_exact(ctx, (const float*)cur.grad, ctx->wf32_bwd[ci], nullptr, (const float*)below.act,
+                               (float*)below.grad, cur.H, cur.W, cur.C, below.C, mask_below ? EPI_MASK : EPI_RAW);
+      } else {
+        rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad,
+                            mask_below ? EPI_MASK : EPI_RAW, 1.f, nullptr);
+      }
+    } else {
+      rc = launch_pool_bwd<T>(ctx, (const T*)below.act, (const T*)cur.grad, (T*)below.grad, below.C, below.H,
+                              below.W, mask_below);
+    }
+    if (rc) return rc;
+  }
+  if (inj[0].on) {
+    CombineArgs a;
+    a.gin = grad_out; a.act = pl->b[0].act; a.fc = inj[0].fc; a.sraw = inj[0].sraw; a.out = grad_out;
+    a.n = pl->b[0].n(); a.apply_mask = 0;
+    a.coef = inj[0].coef; a.h_cc = inj[0].hcc; a.h_sc = inj[0].hsc; a.h_dc = inj[0].hdc;
+    int rc = launch_combine<float>(ctx, a);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+template <typename T>
+static int gram_of_blob(st2_plan* pl, int blob, const float* A, float* D, double* sum_dsq) {
+  st2_ctx* ctx = pl->ctx;
+  Blob& B = pl->b[blob];
+  const long long HW = (long long)B.H * B.W;
+  ST2_CUDA(ctx, cudaMemsetAsync(pl->gram_acc, 0, sizeof(double) * B.C * B.C, ctx->stream));
+  int rc;
+  if (blob == 0) rc = launch_gram_generic<float>(ctx, (const float*)B.act, B.C, HW, 1, HW, pl->gram_acc);
+  else if (B.tc_gram) rc = tc_gram_launch(ctx, B.tc_gram, pl->gram_acc);
+  else rc = launch_gram_generic<T>(ctx, (const T*)B.act, B.C, HW, B.C, 1, pl->gram_acc);
+  if (rc) return rc;
+  return launch_gram_finalize(ctx, pl->gram_acc, A, D, B.C, HW, sum_dsq);
+}
+
+static int ensure(st2_ctx* ctx, void** p, size_t bytes) {
+  if (*p) return 0;
+  ST2_CUDA(ctx, cudaMalloc(p, bytes));
+  return 0;
+}
+
+template <typename T>
+static int eval_impl(st2_plan* pl, const float* x, float* grad_out, int want_grad) {
+  st2_ctx* ctx = pl->ctx;
+  EvalSpec es;
+  memset(&es, 0, sizeof(es));
+  int top = 0;
+  for (int k = 0; k < pl->order_n; ++k) {
+    const int b = pl->order[k];
+    const Blob& B = pl->b[b];
+    if (!(host_w_on(B.cw) || host_w_on(B.sw) || host_w_on(B.dw))) continue;
+    es.order[es.n++] = b;
+    if (b > top) top = b;
+  }
+  for (int b = 0; b < ST2_NUM_BLOBS; ++b) {
+    es.cw[b] = pl->b[b].cw; es.sw[b] = pl->b[b].sw; es.dw[b] = pl->b[b].dw;
+    es.C[b] = pl->b[b].C; es.nelem[b] = (double)pl->b[b].n();
+  }
+  es.tv = pl->tv; es.tv_power = pl->tv_power; es.p = pl->p; es.p_power = pl->p_power;
+  es.N = (double)pl->b[0].n();
+
+  clear_volatile_kernel<<<1, 256, 0, ctx->stream>>>(pl->scal);
+  ST2_LAUNCH_CHECK(ctx);
+  int rc = forward_impl<T>(pl, x, top);
+  if (rc) return rc;
+
+  Inject inj[ST2_NUM_BLOBS];
+  for (int k = 0; k < es.n; ++k) {
+    const int b = es.order[k];
+    Blob& B = pl->b[b];
+    double* sb = pl->scal + b * ST2_SCAL_PER_BLOB;
+    const bool c_on = host_w_on(B.cw), s_on = host_w_on(B.sw), d_on = host_w_on(B.dw);
+    if (c_on && !B.fc) return st2_fail(ctx, ST2_ERR_STATE, "content weight on %s but no content target", g_blobs[b].name);
+    if (s_on && !B.gram_target) return st2_fail(ctx, ST2_ERR_STATE, "style weight on %s but no style target", g_blobs[b].name);
+    if (c_on || d_on) {
+      ProfScope ps(ctx, 5);
+      if (b == 0) rc = launch_feature_sums<float>(ctx, (const float*)B.act, c_on ? (const float*)B.fc : nullptr, B.n(),
+                                                  sb + SB_C_SUMSQ, sb + SB_D_SUMSQ);
+      else rc = launch_feature_sums<T>(ctx, (const T*)B.act, c_on ? (const T*)B.fc : nullptr, B.n(), sb + SB_C_SUMSQ,
+                                       sb + SB_D_SUMSQ);
+      if (rc) return rc;
+    }
+    if (s_on) {
+      const size_t e = (b == 0) ? sizeof(float) : pl->esz;
+      if ((rc = ensure(ctx, (void**)&B.D, sizeof(float) * B.C * B.C))) return rc;
+      if ((rc = ensure(ctx, &B.sraw, e * B.n()))) return rc;
+      {
+        ProfScope ps(ctx, 3);
+        if ((rc = gram_of_blob<T>(pl, b, B.gram_target, B.D, sb + SB_S_GRAMSQ))) return rc;
+      }
+      const long long HW = (long long)B.H * B.W;
+      ProfScope ps(ctx, 4);
+      if (want_grad) {
+        if (b == 0) {
+          rc = launch_style_grad_generic<float>(ctx, (const float*)B.act, B.D, (float*)B.sraw, B.C, HW, 1, HW,
+                                                sb + SB_S_RAWSQ);
+        } else if (pl->prec == ST2_PREC_FP16 && g_blobs[b].kind == KIND_CONV && B.C % 64 == 0) {
+          if ((rc = ensure(ctx, (void**)&B.Dh, sizeof(__half) * B.C * B.C))) return rc;
+          if (!B.tc_style &&
+              (rc = tc_conv_plan_create(ctx, (const __half*)B.act, B.Dh, B.H, B.W, B.C, B.C, 1, &B.tc_style)))
+            return rc;
+          style_scale_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(B.D, B.Dh, B.C, sb);
+          ST2_LAUNCH_CHECK(ctx);
+          rc = tc_conv_launch(ctx, B.tc_style, nullptr, nullptr, (__half*)B.sraw, EPI_RAW, 1.f, sb + SB_S_RAWSQ);
+        } else {
+          rc = launch_style_grad_generic<T>(ctx, (const T*)B.act, B.D, (T*)B.sraw, B.C, HW, B.C, 1, sb + SB_S_RAWSQ);
+        }
+        if (rc) return rc;
+      } else {
+        // loss-only evaluation still freezes the style normaliser (worker.py:265-266), which needs |D F|
+        if (b == 0)
+          rc = launch_style_grad_generic<float>(ctx, (const float*)B.act, B.D, (float*)B.sraw, B.C, HW, 1, HW,
+                                                sb + SB_S_RAWSQ);
+        else
+          rc = launch_style_grad_generic<T>(ctx, (const T*)B.act, B.D, (T*)B.sraw, B.C, HW, B.C, 1, sb + SB_S_RAWSQ);
+        if (rc) return rc;
+      }
+    }
+    inj[b].on = true;
+    inj[b].fc = c_on ? B.fc : nullptr;
+    inj[b].sraw = s_on ? B.sraw : nullptr;
+    inj[b].coef = sb + SB_C_COEF;          // [C_COEF, S_COEF, D_COEF] are consecutive
+  }
+  if (es.n > 0) {
+    ProfScope ps(ctx, 5);
+    coef_kernel<<<1, 32, 0, ctx->stream>>>(es, pl->scal);
+    ST2_LAUNCH_CHECK(ctx);
+  }
+  double* gscal = pl->scal + ST2_SCAL_GLOBAL_BASE;
+  if (want_grad) {
+    if (!grad_out) return st2_fail(ctx, ST2_ERR_ARG, "st2_eval: grad_dev is null");
+    if (es.n > 0) {
+      if ((rc = backward_impl<T>(pl, top, inj, pl->bwd))) return rc;
+    } else {
+      ST2_CUDA(ctx, cudaMemsetAsync(pl->bwd, 0, sizeof(float) * pl->b[0].n(), ctx->stream));
+    }
+    ProfScope ps(ctx, 6);
+    rc = st2_pixel_terms(ctx, x, pl->bwd, grad_out, 3, pl->H, pl->W, pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
+  } else {
+    rc = st2_pixel_terms(ctx, x, nullptr, nullptr, 3, pl->H, pl->W, pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
+  }
+  if (rc) return rc;
+  final_kernel<<<1, 32, 0, ctx->stream>>>(es, pl->scal);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// =============================================================================================
+extern "C" {
+
+int st2_ctx_create(int device, st2_ctx** out) {
+  if (!out) return ST2_ERR_ARG;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return st2_fail(nullptr, ST2_ERR_CUDA, "no CUDA device (%s); libst2 has no CPU fallback",
+                    cudaGetErrorString(e));
+  if (device < 0) device = 0;                    // config.ini `gpu = -1` meant CPU in the reference
+  if (device >= count) return st2_fail(nullptr, ST2_ERR_ARG, "device %d out of range (%d present)", device, count);
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return st2_fail(nullptr, ST2_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return st2_fail(nullptr, ST2_ERR_CUDA, "device %d is sm_%d%d; libst2 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+  st2_ctx* ctx = new st2_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return 0;
+}
+
+void st2_ctx_destroy(st2_ctx* ctx) {
+  if (!ctx) return;
+  for (int i = 0; i < ST2_NUM_CONVS; ++i) {
+    cudaFree(ctx->w_oihw[i]); cudaFree(ctx->bias[i]); cudaFree(ctx->wf32_fwd[i]); cudaFree(ctx->wf32_bwd[i]);
+    cudaFree(ctx->wh_fwd[i]); cudaFree(ctx->wh_bwd[i]);
+  }
+  delete ctx;
+}
+
+const char* st2_last_error(st2_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int st2_set_stream(st2_ctx* ctx, void* s) {
+  if (!ctx) return ST2_ERR_ARG;
+  ctx->stream = (cudaStream_t)s;
+  return 0;
+}
+
+long long st2_launch_count(st2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int st2_profile(st2_ctx* ctx, int enable) {
+  if (!ctx) return ST2_ERR_ARG;
+  ctx->prof_on = enable != 0;
+  return 0;
+}
+
+int st2_profile_read(st2_ctx* ctx, double* ms_out, long long* count_out) {
+  if (!ctx || !ms_out || !count_out) return ST2_ERR_ARG;
+  ST2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < ST2_PROF_CATS; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (auto& sp : ctx->prof_spans) {
+    float ms = 0.f;
+    if (sp.b && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.cat >= 0 && sp.cat < ST2_PROF_CATS) {
+      ms_out[sp.cat] += ms;
+      count_out[sp.cat] += 1;
+    }
+    ctx->prof_pool.push_back(sp.a);
+    if (sp.b) ctx->prof_pool.push_back(sp.b);
+  }
+  ctx->prof_spans.clear();
+  return 0;
+}
+
+int st2_blob_count(void) { return ST2_NUM_BLOBS; }
+const char* st2_blob_name(int b) { return (b >= 0 && b < ST2_NUM_BLOBS) ? g_blobs[b].name : nullptr; }
+int st2_blob_channels(int b) { return (b >= 0 && b < ST2_NUM_BLOBS) ? g_blobs[b].channels : ST2_ERR_ARG; }
+int st2_blob_kind(int b) { return (b >= 0 && b < ST2_NUM_BLOBS) ? g_blobs[b].kind : ST2_ERR_ARG; }
+
+int st2_set_conv_weights(st2_ctx* ctx, int ci, const float* w, const float* b, int cout, int cin) {
+  if (!ctx || ci < 0 || ci >= ST2_NUM_CONVS || !w || !b) return st2_fail(ctx, ST2_ERR_ARG, "st2_set_conv_weights: bad arguments");
+  int blob = -1;
+  for (int i = 0; i < ST2_NUM_BLOBS; ++i) if (g_blobs[i].conv_index == ci) blob = i;
+  const int want_cout = g_blobs[blob].channels, want_cin = g_blobs[blob - 1].channels;
+  if (cout != want_cout || cin != want_cin)
+    return st2_fail(ctx, ST2_ERR_ARG, "%s expects (%d,%d,3,3) weights, got (%d,%d,3,3)", g_blobs[blob].name,
+                    want_cout, want_cin, cout, cin);
+  const size_t nw = (size_t)cout * cin * 9;
+  int rc;
+  if ((rc = ensure(ctx, (void**)&ctx->w_oihw[ci], nw * 4))) return rc;
+  if ((rc = ensure(ctx, (void**)&ctx->bias[ci], (size_t)cout * 4))) return rc;
+  if ((rc = ensure(ctx, (void**)&ctx->wf32_fwd[ci], nw * 4))) return rc;
+  if ((rc = ensure(ctx, (void**)&ctx->wf32_bwd[ci], nw * 4))) return rc;
+  if (ci > 0) {
+    if ((rc = ensure(ctx, (void**)&ctx->wh_fwd[ci], nw * 2))) return rc;
+    if ((rc = ensure(ctx, (void**)&ctx->wh_bwd[ci], nw * 2))) return rc;
+  }
+  ctx->cin[ci] = cin; ctx->cout[ci] = cout;
+  ST2_CUDA(ctx, cudaMemcpyAsync(ctx->w_oihw[ci], w, nw * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ST2_CUDA(ctx, cudaMemcpyAsync(ctx->bias[ci], b, (size_t)cout * 4, cudaMemcpyHostToDevice, ctx->stream));
+  pack_weights_kernel<<<cdiv((long long)nw, 256), 256, 0, ctx->stream>>>(ctx->w_oihw[ci], cout, cin, ctx->wf32_fwd[ci],
+                                                                       ctx->wf32_bwd[ci], ctx->wh_fwd[ci], ctx->wh_bwd[ci]);
+  ST2_LAUNCH_CHECK(ctx);
+  ST2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // host buffers may be freed by the caller
+  return 0;
+}
+
+int st2_plan_create(st2_ctx* ctx, int H, int W, int prec, st2_plan** out) {
+  if (!ctx || !out || H < 1 || W < 1 || (prec != ST2_PREC_FP32 && prec != ST2_PREC_FP16))
+    return st2_fail(ctx, ST2_ERR_ARG, "st2_plan_create: bad arguments");
+  st2_plan* pl = new st2_plan();
+  pl->ctx = ctx; pl->H = H; pl->W = W; pl->prec = prec;
+  pl->esz = prec == ST2_PREC_FP16 ? 2 : 4;
+  int h = H, w = W;
+  for (int i = 0; i < ST2_NUM_BLOBS; ++i) {
+    if (g_blobs[i].kind == KIND_POOL) { h = pool_extent(h); w = pool_extent(w); }
+    pl->b[i].C = g_blobs[i].channels; pl->b[i].H = h; pl->b[i].W = w;
+    pl->order[i] = i;
+    if (i > 0) {
+      ST2_CUDA(ctx, cudaMalloc(&pl->b[i].act, pl->esz * pl->b[i].n()));
+      ST2_CUDA(ctx, cudaMalloc(&pl->b[i].grad, pl->esz * pl->b[i].n()));
+    }
+  }
+  pl->order_n = ST2_NUM_BLOBS;
+  ST2_CUDA(ctx, cudaMalloc(&pl->scal, sizeof(double) * ST2_SCAL_TOTAL));
+  ST2_CUDA(ctx, cudaMemsetAsync(pl->scal, 0, sizeof(double) * ST2_SCAL_TOTAL, ctx->stream));
+  ST2_CUDA(ctx, cudaMalloc(&pl->gram_acc, sizeof(double) * 512 * 512));
+  ST2_CUDA(ctx, cudaMalloc(&pl->bwd, sizeof(float) * pl->b[0].n()));
+  if (prec == ST2_PREC_FP16) {
+    for (int i = 2; i < ST2_NUM_BLOBS; ++i) {
+      if (g_blobs[i].kind != KIND_CONV) continue;
+      const int ci = g_blobs[i].conv_index;
+      if (!ctx->wh_fwd[ci]) return st2_fail(ctx, ST2_ERR_STATE, "load weights before creating an fp16 plan");
+      Blob& cur = pl->b[i];
+      Blob& below = pl->b[i - 1];
+      int rc = tc_conv_plan_create(ctx, (const __half*)below.act, ctx->wh_fwd[ci], cur.H, cur.W, below.C, cur.C, 9, &cur.tc_fwd);
+      if (rc) return rc;
+      rc = tc_conv_plan_create(ctx, (const __half*)cur.grad, ctx->wh_bwd[ci], cur.H, cur.W, cur.C, below.C, 9, &cur.tc_bwd);
+      if (rc) return rc;
+    }
+  }
+  *out = pl;
+  return 0;
+}
+
+void st2_plan_destroy(st2_plan* pl) {
+  if (!pl) return;
+  for (int i = 0; i < ST2_NUM_BLOBS; ++i) {
+    Blob& B = pl->b[i];
+    if (i > 0) { cudaFree(B.act); cudaFree(B.grad); }
+    cudaFree(B.fc); cudaFree(B.sraw); cudaFree(B.inj); cudaFree(B.gram_target); cudaFree(B.D); cudaFree(B.Dh);
+    tc_conv_plan_destroy(B.tc_fwd); tc_conv_plan_destroy(B.tc_bwd); tc_conv_plan_destroy(B.tc_style);
+    tc_gram_plan_destroy(B.tc_gram);
+  }
+  cudaFree(pl->scal); cudaFree(pl->gram_acc); cudaFree(pl->bwd);
+  delete pl;
+}
+
+int st2_plan_blob_dims(st2_plan* pl, int blob, int* c, int* h, int* w) {
+  if (!pl || blob < 0 || blob >= ST2_NUM_BLOBS) return ST2_ERR_ARG;
+  if (c) *c = pl->b[blob].C;
+  if (h) *h = pl->b[blob].H;
+  if (w) *w = pl->b[blob].W;
+  return 0;
+}
+
+int st2_forward(st2_plan* pl, const float* x, int top) {
+  if (!pl || !x || top < 0 || top >= ST2_NUM_BLOBS) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_forward: bad arguments");
+  return pl->prec == ST2_PREC_FP16 ? forward_impl<__half>(pl, x, top) : forward_impl<float>(pl, x, top);
+}
+
+int st2_blob_export(st2_plan* pl, int blob, float* out) {
+  if (!pl || !out || blob < 0 || blob >= ST2_NUM_BLOBS) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_blob_export: bad arguments");
+  st2_ctx* ctx = pl->ctx;
+  if (blob > pl->top_cur) return st2_fail(ctx, ST2_ERR_STATE, "%s not computed by the last forward", g_blobs[blob].name);
+  Blob& B = pl->b[blob];
+  if (blob == 0) {
+    ST2_CUDA(ctx, cudaMemcpyAsync(out, B.act, sizeof(float) * B.n(), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+  }
+  return pl->prec == ST2_PREC_FP16 ? launch_export_nchw<__half>(ctx, (const __half*)B.act, out, B.C, B.H, B.W)
+                                   : launch_export_nchw<float>(ctx, (const float*)B.act, out, B.C, B.H, B.W);
+}
+
+int st2_backward(st2_plan* pl, int n, const int* blobs, const float* const* diffs, float* grad_out) {
+  if (!pl || n < 1 || !blobs || !diffs || !grad_out) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_backward: bad arguments");
+  st2_ctx* ctx = pl->ctx;
+  Inject inj[ST2_NUM_BLOBS];
+  int top = 0;
+  for (int k = 0; k < n; ++k) {
+    const int b = blobs[k];
+    if (b < 0 || b >= ST2_NUM_BLOBS || !diffs[k]) return st2_fail(ctx, ST2_ERR_ARG, "st2_backward: bad blob %d", b);
+    if (b > pl->top_cur) return st2_fail(ctx, ST2_ERR_STATE, "%s not computed by the last forward", g_blobs[b].name);
+    Blob& B = pl->b[b];
+    inj[b].on = true; inj[b].hsc = 1.f;
+    if (b == 0) {
+      inj[b].sraw = diffs[k];
+    } else {
+      int rc = ensure(ctx, &B.inj, pl->esz * B.n());
+      if (rc) return rc;
+      rc = pl->prec == ST2_PREC_FP16 ? launch_import_nchw<__half>(ctx, diffs[k], (__half*)B.inj, B.C, B.H, B.W)
+                                     : launch_import_nchw<float>(ctx, diffs[k], (float*)B.inj, B.C, B.H, B.W);
+      if (rc) return rc;
+      inj[b].sraw = B.inj;
+    }
+    if (b > top) top = b;
+  }
+  return pl->prec == ST2_PREC_FP16 ? backward_impl<__half>(pl, top, inj, grad_out)
+                                   : backward_impl<float>(pl, top, inj, grad_out);
+}
+
+int st2_capture_content(st2_plan* pl, int blob) {
+  if (!pl || blob < 0 || blob >= ST2_NUM_BLOBS) return ST2_ERR_ARG;
+  st2_ctx* ctx = pl->ctx;
+  if (blob > pl->top_cur) return st2_fail(ctx, ST2_ERR_STATE, "%s not computed by the last forward", g_blobs[blob].name);
+  Blob& B = pl->b[blob];
+  const size_t bytes = (blob == 0 ? sizeof(float) : pl->esz) * B.n();
+  int rc = ensure(ctx, &B.fc, bytes);
+  if (rc) return rc;
+  ST2_CUDA(ctx, cudaMemcpyAsync(B.fc, B.act, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+int st2_gram(st2_plan* pl, int blob, float* out) {
+  if (!pl || !out || blob < 0 || blob >= ST2_NUM_BLOBS) return ST2_ERR_ARG;
+  if (blob > pl->top_cur) return st2_fail(pl->ctx, ST2_ERR_STATE, "%s not computed by the last forward", g_blobs[blob].name);
+  return pl->prec == ST2_PREC_FP16 ? gram_of_blob<__half>(pl, blob, nullptr, out, nullptr)
+                                   : gram_of_blob<float>(pl, blob, nullptr, out, nullptr);
+}
+
+int st2_set_style_gram(st2_plan* pl, int blob, const float* gram) {
+  if (!pl || !gram || blob < 0 || blob >= ST2_NUM_BLOBS) return ST2_ERR_ARG;
+  st2_ctx* ctx = pl->ctx;
+  Blob& B = pl->b[blob];
+  int rc = ensure(ctx, (void**)&B.gram_target, sizeof(float) * B.C * B.C);
+  if (rc) return rc;
+  ST2_CUDA(ctx, cudaMemcpyAsync(B.gram_target, gram, sizeof(float) * B.C * B.C, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+int st2_set_blob_weights(st2_plan* pl, int blob, float c, float s, float d) {
+  if (!pl || blob < 0 || blob >= ST2_NUM_BLOBS) return ST2_ERR_ARG;
+  pl->b[blob].cw = c; pl->b[blob].sw = s; pl->b[blob].dw = d;
+  return 0;
+}
+
+int st2_set_eval_order(st2_plan* pl, int n, const int* blobs) {
+  if (!pl || n < 0 || n > ST2_NUM_BLOBS || (n && !blobs)) return ST2_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    if (blobs[i] < 0 || blobs[i] >= ST2_NUM_BLOBS) return st2_fail(pl->ctx, ST2_ERR_ARG, "st2_set_eval_order: bad blob");
+    pl->order[i] = blobs[i];
+  }
+  pl->order_n = n;
+  return 0;
+}
+
+int st2_set_params(st2_plan* pl, float tv, float tv_power, float p, float p_power) {
+  if (!pl) return ST2_ERR_ARG;
+  pl->tv = tv; pl->tv_power = tv_power; pl->p = p; pl->p_power = p_power;
+  return 0;
+}
+
+int st2_reset_norms(st2_plan* pl) {
+  if (!pl) return ST2_ERR_ARG;
+  ST2_CUDA(pl->ctx, cudaMemsetAsync(pl->scal, 0, sizeof(double) * ST2_SCAL_TOTAL, pl->ctx->stream));
+  return 0;
+}
+
+int st2_set_norm(st2_plan* pl, int kind, int blob, double value) {
+  if (!pl || kind < 0 || kind > 2 || blob < 0 || blob >= ST2_NUM_BLOBS) return ST2_ERR_ARG;
+  st2_ctx* ctx = pl->ctx;
+  double* sb = pl->scal + blob * ST2_SCAL_PER_BLOB;
+  const double one = 1.0;
+  ST2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ST2_CUDA(ctx, cudaMemcpy(sb + SB_C_NORM + kind, &value, sizeof(double), cudaMemcpyHostToDevice));
+  ST2_CUDA(ctx, cudaMemcpy(sb + SB_C_VALID + kind, &one, sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int st2_eval(st2_plan* pl, const float* x, float* grad, int want_grad) {
+  if (!pl || !x) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_eval: bad arguments");
+  return pl->prec == ST2_PREC_FP16 ? eval_impl<__half>(pl, x, grad, want_grad)
+                                   : eval_impl<float>(pl, x, grad, want_grad);
+}
+
+int st2_read_scalars(st2_plan* pl, double* host_out) {
+  if (!pl || !host_out) return ST2_ERR_ARG;
+  st2_ctx* ctx = pl->ctx;
+  ST2_CUDA(ctx, cudaMemcpyAsync(host_out, pl->scal, sizeof(double) * ST2_SCAL_TOTAL, cudaMemcpyDeviceToHost, ctx->stream));
+  ST2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int st2_copy_scalars_async(st2_plan* pl, double* pinned_host_out) {
+  if (!pl || !pinned_host_out) return ST2_ERR_ARG;
+  ST2_CUDA(pl->ctx, cudaMemcpyAsync(pinned_host_out, pl->scal, sizeof(double) * ST2_SCAL_TOTAL,
+                                    cudaMemcpyDeviceToHost, pl->ctx->stream));
+  return 0;
+}
+
+double* st2_scalars_dev(st2_plan* pl) { return pl ? pl->scal : nullptr; }
+
+int st2_gram_nchw(st2_ctx* ctx, const float* x, int C, long long HW, float* out) {
+  if (!ctx || !x || !out || C < 1 || HW < 1) return st2_fail(ctx, ST2_ERR_ARG, "st2_gram_nchw: bad arguments");
+  double* acc = nullptr;
+  ST2_CUDA(ctx, cudaMallocAsync(&acc, sizeof(double) * C * C, ctx->stream));
+  ST2_CUDA(ctx, cudaMemsetAsync(acc, 0, sizeof(double) * C * C, ctx->stream));
+  int rc = launch_gram_generic<float>(ctx, x, C, HW, 1, HW, acc);
+  if (!rc) rc = launch_gram_finalize(ctx, acc, nullptr, out, C, HW, nullptr);
+  ST2_CUDA(ctx, cudaFreeAsync(acc, ctx->stream));
+  return rc;
+}
+
+}  // extern "C"

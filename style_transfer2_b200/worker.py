@@ -1,0 +1,542 @@
+#!/usr/bin/env python3
+"""Drop-in worker for style_transfer2: same ZeroMQ/pickle protocol (``messages.py``), same
+``config.ini`` knobs, same layer names, same optimizer step interface -- with the Caffe/NumPy
+compute path replaced by libst2's sm_100a kernels.  Mirrors ``/root/reference/worker.py``:
+``StyleTransfer`` (worker.py:117-315) and ``Worker`` (worker.py:318-409).
+
+Everything from the parameters ``x`` to the next ``x`` stays on the GPU; per iterate only the
+deprocessed image and one block of ~500 scalars (the trace) come back.
+"""
+from collections import OrderedDict
+import ctypes as C
+import logging
+import math
+import sys
+import time
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib, messages, optimizers, utils, vgg
+from .messages import (GetImages, Iterate, PauseIteration, SetImages, SetOptimizer, SetWeights, Shutdown,
+                       StartIteration, WorkerReady)
+from .model import B200Model, Plan
+
+logger = logging.getLogger('worker')
+EPS_W = 1e-15
+
+
+def gram_matrix(x):
+    """worker.py:109-114 for a (1, C, H, W) fp32 CUDA tensor: ``X X^T / (C*H*W)``, on the device."""
+    n, c, h, w = x.shape
+    assert n == 1
+    x = x.contiguous()
+    out = torch.empty((c, c), dtype=torch.float32, device=x.device)
+    utils.default_engine().call('st2_gram_nchw', C.c_void_p(x.data_ptr()), c, h * w, C.c_void_p(out.data_ptr()))
+    return out
+
+
+class LazyTrace:
+    """One evaluation's trace (utils.Trace, utils.py:257-282).  The scalar block is copied to pinned
+    host memory asynchronously when the evaluation is enqueued; the dict is built (and the stream
+    event waited on) the first time ``data`` is read, so evaluations never stall the pipeline."""
+
+    def __init__(self, host_block, event, spec, want_grad, when):
+        self._host, self._event, self._spec = host_block, event, spec
+        self._want_grad, self._when = want_grad, when
+        self._data = None
+        self._extra = []
+
+    def __call__(self, name, value):
+        if self._data is None:
+            self._extra.append((name, value))
+        else:
+            self._put(name, value)
+        return value
+
+    def _put(self, name, value):
+        while name in self._data:
+            name += '_'
+        if isinstance(value, np.floating):
+            value = float(value)
+        elif isinstance(value, np.integer):
+            value = int(value)
+        self._data[name] = value
+
+    @property
+    def data(self):
+        if self._data is None:
+            self._event.synchronize()
+            s = self._host.numpy()
+            self._data = OrderedDict()
+            for b, c_on, s_on, d_on in self._spec:
+                base = b * _lib.SCAL_PER_BLOB
+                name = vgg.BLOBS[b]
+                if c_on:
+                    self._put('%s_c_loss' % name, float(s[base + _lib.SB_C_LOSS]))
+                    self._put('%s_c_grad' % name, float(s[base + _lib.SB_C_GRAD]))
+                if s_on:
+                    self._put('%s_s_loss' % name, float(s[base + _lib.SB_S_LOSS]))
+                    self._put('%s_s_grad' % name, float(s[base + _lib.SB_S_GRAD]))
+                if d_on:
+                    self._put('%s_d_loss' % name, float(s[base + _lib.SB_D_LOSS]))
+                    self._put('%s_d_grad' % name, float(s[base + _lib.SB_D_GRAD]))
+            g = s[_lib.SCAL_GLOBAL_BASE:]
+            self._put('scd_loss', float(g[_lib.G_SCD_LOSS]))
+            self._put('t_loss', float(g[_lib.G_T_LOSS]))
+            self._put('p_loss', float(g[_lib.G_P_LOSS]))
+            if self._want_grad:
+                self._put('scd_grad', float(g[_lib.G_SCD_GRAD]))
+                self._put('t_grad', float(g[_lib.G_T_GRAD]))
+                self._put('p_grad', float(g[_lib.G_P_GRAD]))
+                self._put('time', self._when)
+            self._put('loss', float(g[_lib.G_LOSS]))
+            if self._want_grad:
+                self._put('grad', float(g[_lib.G_GRAD]))
+            for name, value in self._extra:
+                self._put(name, value)
+            self._extra = []
+        return self._data
+
+    @property
+    def loss(self):
+        return self.data['loss']
+
+    def norms(self):
+        """{'c'|'s'|'d': {layer: frozen normaliser}} as of this evaluation."""
+        self.data
+        s = self._host.numpy()
+        out = {k: {} for k in 'cds'}
+        for b in range(_lib.NUM_BLOBS):
+            base = b * _lib.SCAL_PER_BLOB
+            for k, (nf, vf) in zip('csd', ((_lib.SB_C_NORM, _lib.SB_C_VALID), (_lib.SB_S_NORM, _lib.SB_S_VALID),
+                                          (_lib.SB_D_NORM, _lib.SB_D_VALID))):
+                if s[base + vf] != 0.0:
+                    out[k][vgg.BLOBS[b]] = float(s[base + nf])
+        return out
+
+    def __str__(self):
+        return ', '.join('%s: %g' % item for item in self.data.items())
+
+
+class LazyLoss:
+    """Loss of an evaluation; converts to float on demand (``float(loss)``, comparisons, format)."""
+
+    def __init__(self, trace):
+        self.trace = trace
+
+    def __float__(self):
+        return float(self.trace.loss)
+
+    def __repr__(self):
+        return repr(float(self))
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+
+class StyleTransfer:
+    """worker.py:117-315 with device-resident state."""
+
+    TRACE_KEEP = 256
+
+    def __init__(self, model):
+        self.model = model
+        self.engine = model.engine
+        utils.set_default_engine(self.engine)
+        self.is_running = False
+        self.is_starting = False
+        self.t = 0
+        self.input = None              # fp32 CUDA tensor (1, 3, H, W), preprocessed
+        self.content = None            # fp32 CUDA tensor (1, 3, H, W), preprocessed
+        self.style = None              # fp32 CUDA tensor (1, 3, Hs, Ws), preprocessed
+        shape = (len(model.layers()), len(SetWeights.loss_names))
+        self.weights = pd.DataFrame(np.ones(shape), model.layers(), SetWeights.loss_names, np.float32)
+        self.params = {w: 1 for w in SetWeights.scalar_loss_names}
+        self.optimizer = None
+        self.optimizer_cls = optimizers.LBFGSOptimizer
+        self.step_size = SetOptimizer.step_sizes['lbfgs']
+        self.traces = []
+        self._plan = None
+        self._weights_dirty = True
+        self._content_done = set()
+        self._style_done = set()
+        self._pending_norms = {}       # (kind, layer) -> value to install on the next plan sync
+        self._grad_bufs = [None, None]
+        self._grad_turn = 0
+        self._spec = []
+        self._pinned = []
+        self._norm_source = None       # the latest evaluation since the last reset()
+        self._norms_reset = False
+
+    # ------------------------------------------------------------------ reference-compatible views
+    @property
+    def grams(self):
+        """Truthy once a style image is set (worker.py:140-144 only tests truthiness)."""
+        return {'style': self.style} if self.style is not None else None
+
+    @property
+    def features(self):
+        return {'content': self.content} if self.content is not None else None
+
+    @property
+    def norms(self):
+        if self._norm_source is not None:
+            out = self._norm_source.norms()
+        else:
+            out = {k: {} for k in 'cds'}
+        for (kind, layer), v in self._pending_norms.items():
+            out[kind][layer] = v
+        return out
+
+    def set_norms(self, norms):
+        """Install frozen normalisers ({'c'|'s'|'d': {layer: value}}), e.g. from a checkpoint."""
+        for kind, table in norms.items():
+            for layer, v in table.items():
+                self._pending_norms[(kind, layer)] = float(v)
+
+    # ------------------------------------------------------------------ host <-> device plumbing
+    def _upload_image(self, image):
+        """HxWx3 RGB array -> preprocessed (1, 3, H, W) CUDA tensor (CaffeModel.preprocess, worker.py:63-66)."""
+        arr = np.asarray(image)
+        h, w = arr.shape[:2]
+        out = self.engine.empty(1, 3, h, w)
+        if arr.dtype == np.uint8:
+            dev = torch.from_numpy(np.ascontiguousarray(arr)).to(self.engine.device)
+            self.engine.call('st2_preprocess_u8', C.c_void_p(dev.data_ptr()), C.c_void_p(out.data_ptr()), h, w)
+        else:
+            dev = torch.from_numpy(np.ascontiguousarray(arr, np.float32)).to(self.engine.device)
+            self.engine.call('st2_preprocess_f32', C.c_void_p(dev.data_ptr()), C.c_void_p(out.data_ptr()), h, w)
+        return out
+
+    def image(self, x=None):
+        """Deprocessed iterate as an HxWx3 fp32 host array (CaffeModel.deprocess, worker.py:68-71)."""
+        x = self.input if x is None else x
+        h, w = x.shape[2:]
+        hwc = self.engine.empty(h, w, 3)
+        self.engine.call('st2_deprocess', C.c_void_p(x.data_ptr()), C.c_void_p(hwc.data_ptr()), h, w)
+        host = self._pinned_buffer((h, w, 3))
+        host.copy_(hwc, non_blocking=True)
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        return host.numpy()
+
+    def _pinned_buffer(self, shape):
+        for buf in self._pinned:
+            if tuple(buf.shape) == tuple(shape):
+                return buf
+        buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        self._pinned = [buf] + self._pinned[:1]
+        return buf
+
+    # ------------------------------------------------------------------ state machine
+    def check_consistency(self):
+        return bool(self.input is not None and self.content is not None and self.grams
+                    and self.input.shape == self.content.shape)
+
+    def objective_changed(self):
+        if self.optimizer is not None:
+            self.optimizer.objective_changed()
+
+    def pause(self):
+        self.is_running = False
+        self.is_starting = False
+
+    def reset(self):
+        """worker.py:172-175."""
+        self._pending_norms = {}
+        if self._plan is not None:
+            self._plan.reset_norms()
+        self._norms_reset = True
+        self._norm_source = None
+        self.t = 0
+        self.optimizer = self.optimizer_cls(self.input, self.opfunc, step_size=self.step_size)
+
+    def start(self):
+        self.is_starting = True
+        self._start()
+        return self.is_running
+
+    def _start(self):
+        """worker.py:182-189."""
+        if self.is_starting and self.check_consistency():
+            if self.optimizer is None:
+                self.reset()
+            self.is_starting = False
+            self.is_running = True
+
+    def set_input(self, image):
+        """worker.py:191-202."""
+        image = self._upload_image(image)
+        if self.input is not None and self.input.shape == image.shape:
+            self.input.copy_(image)
+            self.objective_changed()
+        elif self.optimizer is not None:
+            self.input = self.optimizer.resample(None, new_x=image)
+            self._start()
+        else:
+            self.input = image
+            self.reset()
+            self._start()
+
+    def set_content(self, image):
+        """worker.py:204-209.  Content features are (re)captured lazily for the layers that carry
+        a content weight, from the stored content image."""
+        self.content = self._upload_image(image)
+        self._content_done = set()
+        self._start()
+        self.objective_changed()
+
+    def set_style(self, image):
+        """worker.py:211-218.  Gram targets are computed lazily for the style-weighted layers."""
+        self.style = self._upload_image(image)
+        self._style_done = set()
+        self._start()
+        self.objective_changed()
+
+    def resample_input(self, size):
+        """worker.py:154-160."""
+        if self.input is not None and self.optimizer is not None:
+            self.input = self.optimizer.resample(tuple(size))
+        else:
+            self.input = self.engine.zeros(1, 3, *size)
+        self._start()
+        self.objective_changed()
+
+    def resample_content(self, size):
+        """worker.py:162-170."""
+        if self.content is not None:
+            self.content = utils.resample_nchw(self.content, tuple(size))
+        else:
+            self.content = self.engine.zeros(1, 3, *size)
+        self._content_done = set()
+        self._start()
+        self.objective_changed()
+
+    def set_step_size(self, step_size):
+        self.step_size = step_size
+        if self.optimizer is not None:
+            self.optimizer.step_size = step_size
+
+    def set_weights(self, weights, params):
+        """worker.py:226-229."""
+        self.weights = pd.DataFrame.from_dict(weights, dtype=np.float32)
+        self.params = params
+        self._weights_dirty = True
+        self.objective_changed()
+
+    # ------------------------------------------------------------------ objective
+    def active_layers(self):
+        """worker.py:234-235: rows with any |w| > 1e-15 (NaN counts as off), in table order."""
+        nonzeros = abs(self.weights) > EPS_W
+        return list(self.weights.index[abs(nonzeros.sum(axis=1)) > EPS_W])
+
+    def _sync_plan(self):
+        h, w = self.input.shape[2:]
+        plan = self.model.plan(h, w)
+        if plan is not self._plan:
+            if self._plan is not None and self._plan.handle and not getattr(self, '_norms_reset', False):
+                for kind, table in self.norms.items():          # norms survive a scale change
+                    for layer, v in table.items():
+                        self._pending_norms.setdefault((kind, layer), v)
+            self._plan = plan
+            plan.reset_norms()
+            self._weights_dirty = True
+            self._content_done, self._style_done = set(), set()
+        self._norms_reset = False
+        if self._weights_dirty:
+            spec, order = [], []
+            table = self.weights
+            for b, name in enumerate(vgg.BLOBS):
+                plan.set_blob_weights(b, 0.0, 0.0, 0.0)
+            for name in self.active_layers():
+                if name not in vgg.BLOB_INDEX:
+                    raise KeyError('unknown layer %r' % name)
+                b = vgg.BLOB_INDEX[name]
+                vals = [float(table[col][name]) if col in table.columns else 0.0
+                        for col in SetWeights.loss_names]
+                vals = [0.0 if (math.isnan(v) or abs(v) <= EPS_W) else v for v in vals]
+                plan.set_blob_weights(b, *vals)
+                order.append(b)
+                spec.append((b, vals[0] != 0.0, vals[1] != 0.0, vals[2] != 0.0))
+            plan.set_eval_order(order)
+            plan.set_params(float(self.params['tv']), float(self.params['tv_power']), float(self.params['p']),
+                            float(self.params['p_power']))
+            self._spec = spec
+            self._weights_dirty = False
+        for (kind, layer), v in list(self._pending_norms.items()):
+            plan.set_norm(kind, vgg.BLOB_INDEX[layer], v)
+        self._pending_norms = {}
+        need_c = [b for b, c_on, _, _ in self._spec if c_on and b not in self._content_done]
+        if need_c:
+            plan.forward(self.content, max(need_c))
+            for b in need_c:
+                plan.capture_content(b)
+                self._content_done.add(b)
+        need_s = [b for b, _, s_on, _ in self._spec if s_on and b not in self._style_done]
+        if need_s:
+            hs, ws = self.style.shape[2:]
+            sp = plan if (hs, ws) == (h, w) else Plan(self.engine, hs, ws, self.model.precision)
+            try:
+                sp.forward(self.style, max(need_s))
+                for b in need_s:
+                    plan.set_style_gram(b, sp.gram(b))
+                    self._style_done.add(b)
+            finally:
+                if sp is not plan:
+                    torch.cuda.current_stream(self.engine.device).synchronize()
+                    sp.close()
+        return plan
+
+    def _next_grad(self):
+        self._grad_turn ^= 1
+        buf = self._grad_bufs[self._grad_turn]
+        if buf is None or buf.shape != self.input.shape:
+            buf = self._grad_bufs[self._grad_turn] = torch.empty_like(self.input)
+        return buf
+
+    def opfunc(self, x, return_grad=True):
+        """worker.py:231-301: objective and gradient at ``x`` (fp32 CUDA tensor).  Returns
+        ``(loss, grad)`` -- ``loss`` converts to float on demand, ``grad`` is a device tensor owned
+        by the caller until the call after next -- or just ``loss`` when ``return_grad`` is false."""
+        self.engine.sync_stream()
+        plan = self._sync_plan()
+        grad = self._next_grad() if return_grad else None
+        plan.eval(x, grad, return_grad)
+        host = torch.empty(_lib.SCAL_TOTAL, dtype=torch.float64, pin_memory=True)
+        plan.copy_scalars_async(host)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.engine.device))
+        tr = LazyTrace(host, ev, list(self._spec), return_grad, time.perf_counter())
+        self.traces.append(tr)
+        self._norm_source = tr
+        if len(self.traces) > self.TRACE_KEEP:
+            del self.traces[:-self.TRACE_KEEP]
+        if not return_grad:
+            return LazyLoss(tr)
+        return LazyLoss(tr), grad
+
+    def step(self, fetch=True):
+        """worker.py:303-310.  ``fetch=False`` skips the device->host copy of the iterate and the
+        trace (device-resident benchmarking)."""
+        self.t += 1
+        x, _ = self.optimizer.step()
+        tr = self.traces[-1]
+        tr('fevals', self.t)
+        if not fetch:
+            return None, None
+        return self.image(x), tr.data
+
+    def write_trace(self, filename):
+        df = pd.DataFrame(t.data for t in self.traces)
+        df.index.name = 'step'
+        df.to_csv(filename)
+
+
+class Worker:
+    """worker.py:318-409: bind PULL on ``worker_socket``, connect PUSH to ``app_socket``, announce
+    ``WorkerReady``, then drain-all-messages-then-one-step until ``Shutdown``."""
+
+    def __init__(self, config, model=None):
+        import zmq
+        self._zmq = zmq
+        self.ctx = zmq.Context.instance()
+        self.sock_in = self.ctx.socket(zmq.PULL)
+        self.sock_out = self.ctx.socket(zmq.PUSH)
+        self.sock_in.bind(config['worker_socket'])
+        self.sock_out.connect(config['app_socket'])
+        self.run_should_stop = False
+        if model is None:
+            base = utils.REPO_DIR
+            gpu = config.getint('gpu', fallback=-1) if hasattr(config, 'getint') else int(config.get('gpu', -1))
+            model = B200Model(base / config.get('prototxt', 'models/vgg19.prototxt'),
+                              base / config.get('caffemodel', 'models/vgg19.caffemodel'), gpu,
+                              precision=config.get('precision', None))
+        self.transfer = StyleTransfer(model)
+        self.sock_out.send_pyobj(WorkerReady(layers=self.transfer.model.layers()))
+
+    def run(self):
+        zmq = self._zmq
+        try:
+            while not self.run_should_stop:
+                if self.transfer.is_running:
+                    try:
+                        while True:
+                            msg = self.sock_in.recv_pyobj(zmq.NOBLOCK)
+                            if self.process_message(msg):
+                                self.run_should_stop = True
+                                break
+                    except zmq.ZMQError:
+                        if self.transfer.is_running:
+                            if self.transfer.check_consistency():
+                                image, trace = self.transfer.step()
+                                self.sock_out.send_pyobj(Iterate(np.array(image), self.transfer.t, dict(trace)))
+                            else:
+                                self.sock_out.send_pyobj(GetImages())
+                    continue
+                msg = self.sock_in.recv_pyobj()
+                if self.process_message(msg):
+                    break
+        except KeyboardInterrupt:
+            pass
+        finally:
+            self.sock_out.send_pyobj(Shutdown())
+
+    def process_message(self, msg):
+        """worker.py:366-409.  Returns True when the loop should end."""
+        def is_image(obj):
+            return obj is not None and not isinstance(obj, int)
+
+        tr = self.transfer
+        if isinstance(msg, SetImages):
+            if is_image(msg.input_image):
+                tr.set_input(msg.input_image)
+            elif msg.input_image == SetImages.RESAMPLE:
+                tr.resample_input(msg.size)
+            if is_image(msg.content_image):
+                tr.set_content(msg.content_image)
+            elif msg.content_image == SetImages.RESAMPLE:
+                tr.resample_content(msg.size)
+            if is_image(msg.style_image):
+                tr.set_style(msg.style_image)
+            if msg.reset_state:
+                tr.reset()
+        elif isinstance(msg, SetOptimizer):
+            tr.optimizer_cls = SetOptimizer.classes[msg.optimizer]
+            tr.set_step_size(msg.step_size)
+            if not isinstance(tr.optimizer, tr.optimizer_cls):
+                tr.reset()
+        elif isinstance(msg, SetWeights):
+            tr.set_weights(msg.weights, msg.params)
+        elif isinstance(msg, Shutdown):
+            return True
+        elif isinstance(msg, StartIteration):
+            if not tr.start():
+                self.sock_out.send_pyobj(GetImages())
+        elif isinstance(msg, PauseIteration):
+            tr.pause()
+        else:
+            logger.error('Invalid message received over ZeroMQ.')
+        return False
+
+
+def main():
+    """worker.py:412-428."""
+    messages.install_as_toplevel()
+    args = utils.parse_args(__doc__)
+    config = utils.read_config(args)
+    debug = args.debug + config.getint('debug', 0)
+    utils.setup_logging(debug)
+    utils.setup_signals()
+    worker = None
+    try:
+        worker = Worker(config)
+        worker.run()
+    finally:
+        logger.info('Shutting down worker process.')
+        if worker is not None:
+            worker.ctx.destroy(0)
+
+
+if __name__ == '__main__':
+    main()
