@@ -63,16 +63,24 @@ class CaffeCPUModel:
 
     mean = np.float32((123.68, 116.779, 103.939)).reshape((3, 1, 1))      # worker.py:34 (RGB)
 
-    def __init__(self, params=None, dtype=torch.float32, full_net=True, threads=None):
+    def __init__(self, params=None, dtype=torch.float32, full_net=True, threads=None, emulate_fp16=False):
         if threads:
             torch.set_num_threads(threads)
         self.dtype = dtype
+        # emulate_fp16: round the operands the way the tensor-core path stores them (weights of
+        # conv1_2.. and every activation / gradient tensor to fp16, round-to-nearest-even; fp32
+        # accumulation) -- separates "precision" from "semantics" when checking that path.
+        self.emulate_fp16 = emulate_fp16
         self.full_net = full_net          # Caffe always runs to pool5 (worker.py:86)
         params = params if params is not None else synthetic_weights(0)
         self.params = OrderedDict(
             (k, (torch.from_numpy(np.ascontiguousarray(w)).to(dtype),
                  torch.from_numpy(np.ascontiguousarray(b)).to(dtype)))
             for k, (w, b) in params.items())
+        if emulate_fp16:
+            for k in list(self.params)[1:]:
+                w, b = self.params[k]
+                self.params[k] = (w.half().to(dtype), b)
         self._act = {}
         self._argmax = {}
 
@@ -104,7 +112,7 @@ class CaffeCPUModel:
             for name, kind, _ in TOPOLOGY[1:]:
                 if kind == 'conv':
                     w, b = self.params[name]
-                    cur = F.relu(F.conv2d(cur, w, b, padding=1))
+                    cur = self._q(F.relu(F.conv2d(cur, w, b, padding=1)))
                 else:
                     cur, idx = F.max_pool2d(cur, 2, 2, ceil_mode=True, return_indices=True)
                     self._argmax[name] = idx
@@ -115,6 +123,9 @@ class CaffeCPUModel:
         for name in want:
             out[name] = self._act[name].to(torch.float32).numpy()
         return out
+
+    def _q(self, t):
+        return t.half().to(self.dtype) if self.emulate_fp16 else t
 
     # -- worker.py:88-106
     def backward(self, diffs):
@@ -137,12 +148,14 @@ class CaffeCPUModel:
                     if inj is not None:
                         g = inj if g is None else g + inj                 # blob.diff += diffs[l]
                     w, _ = self.params[name]
-                    g = F.conv_transpose2d(g, w, padding=1)               # data gradient only
+                    g = F.conv_transpose2d(self._q(g), w, padding=1)      # data gradient only
+                    if idx > 1:
+                        g = self._q(g)
                 else:
                     if inj is not None:
                         g = inj if g is None else g + inj
                     shape = self._act[below].shape
-                    g = F.max_unpool2d(g, self._argmax[name], 2, 2, output_size=shape[-2:])
+                    g = F.max_unpool2d(self._q(g), self._argmax[name], 2, 2, output_size=shape[-2:])
             if 'data' in diffs:
                 d0 = torch.from_numpy(np.ascontiguousarray(diffs['data'])).to(self.dtype)
                 g = d0 if g is None else g + d0

@@ -121,13 +121,16 @@ def test_forward_odd_sizes_ceil_mode(models):
 
 @pytest.mark.parametrize('layers', [['conv2_1'], ['conv4_2', 'conv1_1', 'conv3_1'], ['pool2', 'conv3_2', 'data'],
                                     ['pool5', 'conv5_4'], ['data'], ['conv1_1']])
-@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('fp16', 2e-2)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('fp16', 1e-2)])
 def test_backward_segment_semantics(models, layers, precision, tol):
-    """Injected diffs enter below the layer's own ReLU; gradient from above is masked."""
+    """Injected diffs enter below the layer's own ReLU; gradient from above is masked.
+    The data gradient is DISCONTINUOUS in the features (ReLU masks, pool arg-max): a fraction f of
+    flipped decisions costs ~sqrt(f) relative error, so the fp16 path is checked against the oracle
+    with the same operand rounding (semantics), and against the fp32 oracle only loosely."""
     from oracle.caffe_cpu import CaffeCPUModel
     rs = np.random.RandomState(11)
     x = (rs.rand(1, 3, 37, 45) * 255 - 120).astype(np.float32)
-    ref = CaffeCPUModel()
+    ref = CaffeCPUModel(emulate_fp16=(precision == 'fp16'))
     feats = ref.forward(x)
     diffs = {l: rs.randn(*feats[l].shape).astype(np.float32) for l in layers}
     want = ref.backward(diffs)
