@@ -305,15 +305,3 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     default:  return launch_bn<64>(ctx, p, bias, act, out, epi, out_scale, sumsq);
   }
 }
-
-// ---- tcgen05 Gram (st2_gram_tc.cu provides the real one once enabled) --------------------------
-#ifndef ST2_HAVE_TC_GRAM
-struct TcGramPlan { int unused; };
-int tc_gram_plan_create(st2_ctx* ctx, const __half*, int, long long, TcGramPlan**) {
-  return st2_fail(ctx, ST2_ERR_UNSUPPORTED, "tcgen05 Gram not built");
-}
-void tc_gram_plan_destroy(TcGramPlan* p) { delete p; }
-int tc_gram_launch(st2_ctx* ctx, TcGramPlan*, double*) {
-  return st2_fail(ctx, ST2_ERR_UNSUPPORTED, "tcgen05 Gram not built");
-}
-#endif

@@ -1,0 +1,231 @@
+// tcgen05 Gram matrix of fp16 NHWC features (K5 of SURVEY 2.4):  G[i, j] = sum_p F[p, i] F[p, j].
+//
+// F is stored pixel-major ([HW][C], channels contiguous), so both operands of F^T F are "MN-major":
+// the TMA box {64 channels, 64 pixels} lands in shared memory as 64 K-rows (pixels) of 128 bytes
+// (64 channels), SWIZZLE_128B -- the UMMA canonical MN-major layout with 8-row atoms 1024 B apart
+// (SBO) and 64-channel groups 8 KB apart (LBO).  No transposed copy of F is ever made.
+// One CTA = one 128 x GN tile of G over one chunk of pixels (split-K across the whole GPU); fp32
+// accumulators live in TMEM; partial tiles go to a workspace with plain 128-byte row stores and are
+// summed (in double) by the finalize kernel -- deterministic, no atomics.
+#include "st2_kernels.h"
+#include "st2_tc.cuh"
+
+int st2_encode_tmap(st2_ctx* ctx, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box);
+
+namespace {
+
+constexpr int GM = 128;
+constexpr int KP = 64;              // pixels per pipeline stage
+constexpr int kBoxBytes = 64 * 64 * 2;   // one {64 ch, 64 px} box = 8 KB
+constexpr int kThreadsG = 256;
+
+template <int GN> struct GCfg {
+  static constexpr int kABytes = 2 * kBoxBytes;
+  static constexpr int kBBytes = (GN / 64) * kBoxBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (GN == 256) ? 4 : (GN == 128 ? 6 : 8);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct GramGeom {
+  int C;
+  long long HW;
+  long long chunk;     // pixels per split (multiple of 64)
+  int m_tiles, n_tiles, splits;
+};
+
+template <int GN>
+__global__ void __launch_bounds__(kThreadsG, 1)
+tc_gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramGeom g, float* __restrict__ partials) {
+  using C = GCfg<GN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* done_bar = bars + 2 * C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
+  const int m0 = mt * GM, n0 = nt * GN;
+  const long long p_begin = (long long)split * g.chunk;
+  const long long p_end = (p_begin + g.chunk < g.HW) ? p_begin + g.chunk : g.HW;
+  const int k_iters = (int)((p_end - p_begin + KP - 1) / KP);
+
+  if (warp == 0 && lane == 0) tc::prefetch_tmap(&tmap);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(done_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, GN < 32 ? 32 : GN);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        const int p = (int)(p_begin + (long long)it * KP);
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        tc::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          int ca = m0 + a * 64;
+          if (ca > g.C - 64) ca = g.C - 64;               // C == 64: rows 64..127 duplicate rows 0..63 (discarded)
+          tc::tma_load_2d(smem_a + stage * C::kABytes + a * kBoxBytes, &tmap, &full_bar[stage], ca, p);
+        }
+#pragma unroll
+        for (int b = 0; b < GN / 64; ++b)
+          tc::tma_load_2d(smem_b + stage * C::kBBytes + b * kBoxBytes, &tmap, &full_bar[stage], n0 + b * 64, p);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_f16(GM, GN, 1, 1);      // both operands MN-major
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(smem_a + stage * C::kABytes);
+        const uint32_t b_addr = tc::smem_u32(smem_b + stage * C::kBBytes);
+#pragma unroll
+        for (int k = 0; k < KP / 16; ++k) {                        // 16 pixels = 2 atoms of 8 K-rows = 2048 B
+          const uint64_t a_desc = tc::smem_desc_mn_sw128(a_addr + k * 2048, kBoxBytes);
+          const uint64_t b_desc = tc::smem_desc_mn_sw128(b_addr + k * 2048, kBoxBytes);
+          tc::umma_f16(tmem_base, a_desc, b_desc, idesc, (it | k) != 0);
+        }
+        tc::umma_commit(&empty_bar[stage]);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      tc::umma_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int i = m0 + ew * 32 + lane;
+    tc::mbar_wait(done_bar, 0);
+    tc::fence_after_sync();
+    const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16);
+    float* dst = partials + ((long long)split * g.C + i) * g.C + n0;
+#pragma unroll 1
+    for (int c = 0; c < GN / 32; ++c) {
+      uint32_t r[32];
+      tc::tmem_ld_32x32(t_row + c * 32, r);
+      tc::tmem_ld_wait();
+      if (i < g.C && k_iters > 0) {
+        float4* o = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          o[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, GN < 32 ? 32 : GN);
+  }
+}
+
+// D = (sum_s partial[s]) / (C*HW) - A ; sum D^2
+__global__ void gram_finalize_partials_kernel(const float* __restrict__ partials, int nsplit,
+                                              const float* __restrict__ A, float* __restrict__ D, int C,
+                                              long long HW, double* sum_dsq) {
+  const long long n = (long long)C * C;
+  const float denom = (float)((double)C * (double)HW);
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += (double)partials[(long long)k * n + i];
+    float gv = (float)s / denom;
+    if (A != nullptr) gv -= A[i];
+    D[i] = gv;
+    acc = fmaf(gv, gv, acc);
+  }
+  float v[1] = {acc};
+  double* dst[1] = {sum_dsq};
+  block_accumulate<1>(v, dst);
+}
+
+}  // namespace
+
+struct TcGramPlan {
+  CUtensorMap tmap;
+  GramGeom g;
+  int gn;
+  float* partials;
+};
+
+int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGramPlan** out) {
+  if (C % 64 || C < 64 || HW < 1) return st2_fail(ctx, ST2_ERR_ARG, "tc_gram: C must be a multiple of 64");
+  TcGramPlan* p = new TcGramPlan();
+  p->gn = (C % 256 == 0) ? 256 : (C % 128 == 0 ? 128 : 64);
+  GramGeom& g = p->g;
+  g.C = C; g.HW = HW;
+  g.m_tiles = (C + GM - 1) / GM;
+  g.n_tiles = C / p->gn;
+  const int tiles = g.m_tiles * g.n_tiles;
+  long long want = ctx->sm_count / tiles;
+  if (want < 1) want = 1;
+  long long chunk = (HW + want - 1) / want;
+  chunk = (chunk + KP - 1) / KP * KP;
+  g.chunk = chunk;
+  g.splits = (int)((HW + chunk - 1) / chunk);
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)HW};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)KP};
+  int rc = st2_encode_tmap(ctx, &p->tmap, F, 2, dims, strides, box);
+  if (rc) { delete p; return rc; }
+  cudaError_t e = cudaMalloc(&p->partials, sizeof(float) * (size_t)g.splits * C * C);
+  if (e != cudaSuccess) { delete p; return st2_fail(ctx, ST2_ERR_CUDA, "tc_gram: workspace: %s", cudaGetErrorString(e)); }
+  *out = p;
+  return 0;
+}
+
+void tc_gram_plan_destroy(TcGramPlan* p) {
+  if (!p) return;
+  cudaFree(p->partials);
+  delete p;
+}
+
+template <int GN>
+static int launch_gn(st2_ctx* ctx, TcGramPlan* p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_gram_kernel<GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GCfg<GN>::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(p->g.m_tiles * p->g.n_tiles, p->g.splits);
+  tc_gram_kernel<GN><<<grid, kThreadsG, GCfg<GN>::kSmemBytes, ctx->stream>>>(p->tmap, p->g, p->partials);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double* sum_dsq) {
+  int rc;
+  switch (p->gn) {
+    case 256: rc = launch_gn<256>(ctx, p); break;
+    case 128: rc = launch_gn<128>(ctx, p); break;
+    default:  rc = launch_gn<64>(ctx, p); break;
+  }
+  if (rc) return rc;
+  const long long n = (long long)p->g.C * p->g.C;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+  gram_finalize_partials_kernel<<<blocks, 256, 0, ctx->stream>>>(p->partials, p->g.splits, A, D, p->g.C, p->g.HW,
+                                                                 sum_dsq);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}

@@ -69,4 +69,13 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
 struct TcGramPlan;
 int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGramPlan** out);
 void tc_gram_plan_destroy(TcGramPlan* p);
-int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, double* Gd);
+// D = F^T F / (C*HW) - A (A nullable); *sum_dsq += sum D^2 (nullable)
+int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double* sum_dsq);
+
+// ---- st2_elementwise.cu: 16-byte-vectorised variants (fall back to the scalar kernels) ---------
+template <typename T> int launch_pool_fwd_v(st2_ctx* ctx, const T* in, T* out, int C, int H, int W);
+template <typename T>
+int launch_pool_bwd_v(st2_ctx* ctx, const T* act, const T* g_pool, T* g_out, int C, int H, int W, int apply_mask);
+template <typename T> int launch_combine_v(st2_ctx* ctx, const CombineArgs& a);
+template <typename T>
+int launch_feature_sums_v(st2_ctx* ctx, const T* act, const T* fc, long long n, double* sum_diff_sq, double* sum_sq);

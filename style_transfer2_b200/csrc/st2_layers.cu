@@ -15,82 +15,153 @@ inline int ew_grid(long long work_items, int sm_count) {
 }
 
 // =============================================================================== conv1_1 forward
-// One block: 64 consecutive pixels of one row x 64 output channels.  Thread = (pixel, 16 couts).
+// Work item: 128 consecutive pixels of one row.  Thread = (pixel, 32 of the 64 couts): 27 inputs in
+// registers, weights read from shared memory as warp-broadcast float4, 64-byte (fp16) or 128-byte
+// (fp32) contiguous store per thread.  Grid-stride over work items so the 6.9 KB weight tile is
+// staged once per block.  FMA-bound: 1728 FMA per pixel.
 template <typename T>
-__global__ void conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                      const float* __restrict__ bias, T* __restrict__ out, int H, int W) {
-  __shared__ float sw[27 * 64];
-  __shared__ float sb[64];
-  __shared__ float sx[3][3][66];
-  const int tiles_w = (W + 63) / 64;
-  const int h = blockIdx.x / tiles_w;
-  const int w0 = (blockIdx.x % tiles_w) * 64;
+__global__ void __launch_bounds__(256)
+conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ bias, T* __restrict__ out, int H, int W) {
+  __shared__ __align__(16) float sw[27 * 64];          // [tap][ci][co]
+  __shared__ __align__(16) float sb[64];
+  __shared__ float sx[3][3][130];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  for (int i = threadIdx.x; i < 3 * 3 * 66; i += blockDim.x) {
-    const int c = i / (3 * 66), r = (i / 66) % 3, col = i % 66;
-    const int hh = h + r - 1, ww = w0 + col - 1;
-    float v = 0.f;
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((long long)c * H + hh) * W + ww];
-    sx[c][r][col] = v;
-  }
-  __syncthreads();
-  const int px = threadIdx.x & 63, cg = threadIdx.x >> 6;
-  const int ww = w0 + px;
-  if (ww >= W) return;
-  float acc[16];
+  const int tiles_w = (W + 127) / 128;
+  const int items = H * tiles_w;
+  const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int h = item / tiles_w;
+    const int w0 = (item - h * tiles_w) * 128;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 3 * 130; i += blockDim.x) {
+      const int c = i / (3 * 130), r = (i / 130) % 3, col = i % 130;
+      const int hh = h + r - 1, ww = w0 + col - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[((long long)c * H + hh) * W + ww]);
+      sx[c][r][col] = v;
+    }
+    __syncthreads();
+    const int ww = w0 + px;
+    if (ww >= W) continue;
+    float acc[32];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = sb[cg * 16 + j];
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
+    for (int j = 0; j < 32; ++j) acc[j] = sb[half * 32 + j];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const float v = sx[c][r][px + s];
-        const float* wr = &sw[((r * 3 + s) * 3 + c) * 64 + cg * 16];     // [tap][ci][co]
+      for (int s = 0; s < 3; ++s)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        for (int c = 0; c < 3; ++c) {
+          const float v = sx[c][r][px + s];
+          const float4* wr = reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + c) * 64 + half * 32]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 wv = wr[q];
+            acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+          }
+        }
+    T* o = out + ((long long)h * W + ww) * 64 + half * 32;
+    if (sizeof(T) == 2) {
+      uint4* op = reinterpret_cast<uint4*>(o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        __half2* hp = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          hp[e] = __floats2half2_rn(fmaxf(acc[8 * q + 2 * e], 0.f), fmaxf(acc[8 * q + 2 * e + 1], 0.f));
+        op[q] = u;
       }
-  T* o = out + ((long long)h * W + ww) * 64 + cg * 16;
+    } else {
+      float4* op = reinterpret_cast<float4*>(o);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] = from_f<T>(fmaxf(acc[j], 0.f));
+      for (int q = 0; q < 8; ++q)
+        op[q] = make_float4(fmaxf(acc[4 * q], 0.f), fmaxf(acc[4 * q + 1], 0.f), fmaxf(acc[4 * q + 2], 0.f),
+                            fmaxf(acc[4 * q + 3], 0.f));
+    }
+  }
 }
 
 // =============================================================================== conv1_1 dgrad
 // gx[ci][h][w] = sum_{tap,co} g[h+1-r][w+1-s][co] * W[co][ci][r][s];  w_bwd = [tap'][co][ci] with
 // tap' already flipped so the kernel reads g at (h + r' - 1, w + s' - 1).
+// Eight lanes share a pixel, each owning 8 of the 64 channels: a warp's 16-byte loads cover four
+// whole 128-byte pixel rows (fully coalesced), the 8x3 weights of a lane's channel group come from
+// shared memory as float4, and the three outputs are reduced across the 8 lanes with shuffles.
+template <typename T> struct Load8 {};
+template <> struct Load8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hp[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  }
+};
+template <> struct Load8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 template <typename T>
-__global__ void conv_first_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w,
-                                      float* __restrict__ gx, int H, int W) {
-  __shared__ float sw[9 * 64 * 3];
-  for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) sw[i] = w[i];
+__global__ void __launch_bounds__(256)
+conv_first_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int H,
+                      int W) {
+  __shared__ __align__(16) float sw[9][8][24];          // [tap][channel group][8 co x 3 ci]
+  for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) {
+    const int ci = i % 3, co = (i / 3) % 64, tap = i / 192;
+    sw[tap][co >> 3][(co & 7) * 3 + ci] = w[i];
+  }
   __syncthreads();
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= (long long)H * W) return;
-  const int h = (int)(p / W), ww = (int)(p % W);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int r = 0; r < 3; ++r) {
-    const int hh = h + r - 1;
-    if (hh < 0 || hh >= H) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int wc = ww + s - 1;
-      if (wc < 0 || wc >= W) continue;
-      const T* gp = g + ((long long)hh * W + wc) * 64;
-      const float* wr = &sw[(r * 3 + s) * 64 * 3];
-#pragma unroll 8
-      for (int co = 0; co < 64; ++co) {
-        const float v = to_f<T>(gp[co]);
-        a0 = fmaf(v, wr[co * 3 + 0], a0);
-        a1 = fmaf(v, wr[co * 3 + 1], a1);
-        a2 = fmaf(v, wr[co * 3 + 2], a2);
+  const long long HW = (long long)H * W;
+  const int sub = threadIdx.x >> 3, cgp = threadIdx.x & 7;       // 32 pixels per block pass
+  const long long stride = (long long)gridDim.x * 32;
+  for (long long base = (long long)blockIdx.x * 32; base < HW; base += stride) {   // block-uniform trip count
+    const long long p = base + sub;
+    const bool live = p < HW;
+    const int h = live ? (int)(p / W) : 0, ww = live ? (int)(p - (long long)h * W) : 0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = h + r - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int wc = ww + s - 1;
+          if (wc < 0 || wc >= W) continue;
+          float v[8];
+          Load8<T>::load(g + ((long long)hh * W + wc) * 64 + cgp * 8, v);
+          const float4* wr = reinterpret_cast<const float4*>(&sw[r * 3 + s][cgp][0]);
+          float wv[24];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const float4 t4 = wr[q];
+            wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a0 = fmaf(v[e], wv[3 * e + 0], a0);
+            a1 = fmaf(v[e], wv[3 * e + 1], a1);
+            a2 = fmaf(v[e], wv[3 * e + 2], a2);
+          }
+        }
       }
     }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (live && cgp < 3) gx[(long long)cgp * HW + p] = cgp == 0 ? a0 : (cgp == 1 ? a1 : a2);
   }
-  const long long HW = (long long)H * W;
-  gx[p] = a0;
-  gx[HW + p] = a1;
-  gx[2 * HW + p] = a2;
 }
 
 // =============================================================================== exact fp32 conv
@@ -421,7 +492,8 @@ __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restric
 template <typename T>
 int launch_conv_first_fwd(st2_ctx* ctx, const float* x, const float* w, const float* bias, T* out, int H,
                           int W) {
-  const int blocks = H * ((W + 63) / 64);
+  const int items = H * ((W + 127) / 128);
+  const int blocks = items < ctx->sm_count * 4 ? items : ctx->sm_count * 4;
   conv_first_fwd_kernel<T><<<blocks, 256, 0, ctx->stream>>>(x, w, bias, out, H, W);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
@@ -432,7 +504,9 @@ template int launch_conv_first_fwd<__half>(st2_ctx*, const float*, const float*,
 template <typename T>
 int launch_conv_first_bwd(st2_ctx* ctx, const T* g, const float* w, float* gx, int H, int W) {
   const long long hw = (long long)H * W;
-  conv_first_bwd_kernel<T><<<cdiv(hw, 128), 128, 0, ctx->stream>>>(g, w, gx, H, W);
+  long long blocks = (hw + 31) / 32;
+  if (blocks > (long long)ctx->sm_count * 8) blocks = (long long)ctx->sm_count * 8;
+  conv_first_bwd_kernel<T><<<(int)blocks, 256, 0, ctx->stream>>>(g, w, gx, H, W);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }

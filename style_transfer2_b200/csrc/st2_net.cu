@@ -4,6 +4,7 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 // --------------------------------------------------------------------------------------------
@@ -234,7 +235,7 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
         rc = tc_conv_launch(ctx, cur.tc_fwd, ctx->bias[ci], nullptr, (__half*)cur.act, EPI_BIAS_RELU, 1.f, nullptr);
       }
     } else {
-      rc = launch_pool_fwd<T>(ctx, (const T*)below.act, (T*)cur.act, below.C, below.H, below.W);
+      rc = launch_pool_fwd_v<T>(ctx, (const T*)below.act, (T*)cur.act, below.C, below.H, below.W);
     }
     if (rc) return rc;
   }
@@ -265,7 +266,7 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
       a.apply_mask = is_conv ? 1 : 0;
       a.coef = inj[i].coef; a.h_cc = inj[i].hcc; a.h_sc = inj[i].hsc; a.h_dc = inj[i].hdc;
       ProfScope ps(ctx, 5);
-      rc = launch_combine<T>(ctx, a);
+      rc = launch_combine_v<T>(ctx, a);
       if (rc) return rc;
     } else if (!have_above) {
       return st2_fail(ctx, ST2_ERR_STATE, "top blob carries no diff");
@@ -287,7 +288,7 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
                             mask_below ? EPI_MASK : EPI_RAW, 1.f, nullptr);
       }
     } else {
-      rc = launch_pool_bwd<T>(ctx, (const T*)below.act, (const T*)cur.grad, (T*)below.grad, below.C, below.H,
+      rc = launch_pool_bwd_v<T>(ctx, (const T*)below.act, (const T*)cur.grad, (T*)below.grad, below.C, below.H,
                               below.W, mask_below);
     }
     if (rc) return rc;
@@ -297,7 +298,7 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
     a.gin = grad_out; a.act = pl->b[0].act; a.fc = inj[0].fc; a.sraw = inj[0].sraw; a.out = grad_out;
     a.n = pl->b[0].n(); a.apply_mask = 0;
     a.coef = inj[0].coef; a.h_cc = inj[0].hcc; a.h_sc = inj[0].hsc; a.h_dc = inj[0].hdc;
-    int rc = launch_combine<float>(ctx, a);
+    int rc = launch_combine_v<float>(ctx, a);
     if (rc) return rc;
   }
   return 0;
@@ -308,10 +309,17 @@ static int gram_of_blob(st2_plan* pl, int blob, const float* A, float* D, double
   st2_ctx* ctx = pl->ctx;
   Blob& B = pl->b[blob];
   const long long HW = (long long)B.H * B.W;
+  if (blob != 0 && pl->prec == ST2_PREC_FP16 && g_blobs[blob].kind == KIND_CONV && B.C % 64 == 0 &&
+      !getenv("ST2_NO_TC_GRAM")) {
+    if (!B.tc_gram) {
+      int rc0 = tc_gram_plan_create(ctx, (const __half*)B.act, B.C, HW, &B.tc_gram);
+      if (rc0) return rc0;
+    }
+    return tc_gram_launch(ctx, B.tc_gram, A, D, sum_dsq);
+  }
   ST2_CUDA(ctx, cudaMemsetAsync(pl->gram_acc, 0, sizeof(double) * B.C * B.C, ctx->stream));
   int rc;
   if (blob == 0) rc = launch_gram_generic<float>(ctx, (const float*)B.act, B.C, HW, 1, HW, pl->gram_acc);
-  else if (B.tc_gram) rc = tc_gram_launch(ctx, B.tc_gram, pl->gram_acc);
   else rc = launch_gram_generic<T>(ctx, (const T*)B.act, B.C, HW, B.C, 1, pl->gram_acc);
   if (rc) return rc;
   return launch_gram_finalize(ctx, pl->gram_acc, A, D, B.C, HW, sum_dsq);
@@ -358,9 +366,9 @@ static int eval_impl(st2_plan* pl, const float* x, float* grad_out, int want_gra
     if (s_on && !B.gram_target) return st2_fail(ctx, ST2_ERR_STATE, "style weight on %s but no style target", g_blobs[b].name);
     if (c_on || d_on) {
       ProfScope ps(ctx, 5);
-      if (b == 0) rc = launch_feature_sums<float>(ctx, (const float*)B.act, c_on ? (const float*)B.fc : nullptr, B.n(),
+      if (b == 0) rc = launch_feature_sums_v<float>(ctx, (const float*)B.act, c_on ? (const float*)B.fc : nullptr, B.n(),
                                                   sb + SB_C_SUMSQ, sb + SB_D_SUMSQ);
-      else rc = launch_feature_sums<T>(ctx, (const T*)B.act, c_on ? (const T*)B.fc : nullptr, B.n(), sb + SB_C_SUMSQ,
+      else rc = launch_feature_sums_v<T>(ctx, (const T*)B.act, c_on ? (const T*)B.fc : nullptr, B.n(), sb + SB_C_SUMSQ,
                                        sb + SB_D_SUMSQ);
       if (rc) return rc;
     }

@@ -20,7 +20,7 @@ constexpr int kVec = 4;
 
 inline int grid_for(long long n, int sm_count) {
   long long blocks = (n + (long long)kThreads * kVec - 1) / ((long long)kThreads * kVec);
-  long long cap = (long long)sm_count * 8;
+  long long cap = (long long)sm_count * 6;
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
@@ -43,119 +43,160 @@ __device__ __forceinline__ const float* slot_ptr(const float* base, long long n,
   return base + (long long)((head + logical) % slots) * n;
 }
 
+// V floats per access: 4 (16-byte vectors, when n % 4 == 0) or 1
+template <int V> struct Pack { float v[V]; };
+template <int V> __device__ __forceinline__ Pack<V> ld(const float* p, long long i);
+template <> __device__ __forceinline__ Pack<1> ld<1>(const float* p, long long i) { Pack<1> r; r.v[0] = p[i]; return r; }
+template <> __device__ __forceinline__ Pack<4> ld<4>(const float* p, long long i) {
+  const float4 u = reinterpret_cast<const float4*>(p)[i];
+  Pack<4> r; r.v[0] = u.x; r.v[1] = u.y; r.v[2] = u.z; r.v[3] = u.w; return r;
+}
+template <int V> __device__ __forceinline__ void st(float* p, long long i, const Pack<V>& a);
+template <> __device__ __forceinline__ void st<1>(float* p, long long i, const Pack<1>& a) { p[i] = a.v[0]; }
+template <> __device__ __forceinline__ void st<4>(float* p, long long i, const Pack<4>& a) {
+  reinterpret_cast<float4*>(p)[i] = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+
+#define ST2_PACK_LOOP(k, npk) \
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < (npk); k += (long long)gridDim.x * blockDim.x)
+
 // acc1[0] = (count > 0) ? S_newest . g : g . g
-__global__ void lbfgs_first_dot(LbfgsDev* st, const float* __restrict__ S, const float* __restrict__ g,
+template <int V>
+__global__ void lbfgs_first_dot(LbfgsDev* st_, const float* __restrict__ S, const float* __restrict__ g,
                                 long long n, int slots) {
-  const int count = st->count;
-  const float* a = count > 0 ? slot_ptr(S, n, slots, st->head, count - 1) : g;
+  const int count = st_->count;
+  const float* a = count > 0 ? slot_ptr(S, n, slots, st_->head, count - 1) : g;
   float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    acc += a[i] * g[i];
+  ST2_PACK_LOOP(k, n / V) {
+    const Pack<V> av = ld<V>(a, k), gv = ld<V>(g, k);
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc = fmaf(av.v[e], gv.v[e], acc);
+  }
   float v[1] = {acc};
-  double* dst[1] = {&st->acc1[0]};
+  double* dst[1] = {&st_->acc1[0]};
   block_accumulate<1>(v, dst);
 }
 
 // loop-1 step j (logical i = count-1-j).  q_out = src - alpha_i * Y_i, then the next dot.
-__global__ void lbfgs_loop1(LbfgsDev* st, const float* __restrict__ S, const float* __restrict__ Y,
+template <int V>
+__global__ void lbfgs_loop1(LbfgsDev* st_, const float* __restrict__ S, const float* __restrict__ Y,
                             const float* __restrict__ g, float* __restrict__ q, long long n, int slots,
                             int j) {
-  const int count = st->count;
+  const int count = st_->count;
   const int i = count - 1 - j;
   if (i < 0) return;
-  const int head = st->head;
+  const int head = st_->head;
   const int phys = (head + i) % slots;
-  const double alpha_d = st->acc1[j] / st->sy[phys];
-  if (blockIdx.x == 0 && threadIdx.x == 0) st->alpha[i] = alpha_d;
+  const double alpha_d = st_->acc1[j] / st_->sy[phys];
+  if (blockIdx.x == 0 && threadIdx.x == 0) st_->alpha[i] = alpha_d;
   const float na = -(float)alpha_d;
   const float* src = (j == 0) ? g : q;
   const float* y = Y + (long long)phys * n;
   const float* nxt = (i > 0) ? slot_ptr(S, n, slots, head, i - 1) : slot_ptr(Y, n, slots, head, 0);
   float acc = 0.f;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-       k += (long long)gridDim.x * blockDim.x) {
-    float v = fmaf(na, y[k], src[k]);
-    q[k] = v;
-    acc += nxt[k] * v;
+  ST2_PACK_LOOP(k, n / V) {
+    const Pack<V> yv = ld<V>(y, k), sv = ld<V>(src, k), nv = ld<V>(nxt, k);
+    Pack<V> o;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      o.v[e] = fmaf(na, yv.v[e], sv.v[e]);
+      acc = fmaf(nv.v[e], o.v[e], acc);
+    }
+    st<V>(q, k, o);
   }
   float v[1] = {acc};
-  double* dst[1] = {(i > 0) ? &st->acc1[j + 1] : &st->acc_mid};
+  double* dst[1] = {(i > 0) ? &st_->acc1[j + 1] : &st_->acc_mid};
   block_accumulate<1>(v, dst);
 }
 
 // no history: q = g / sqrt(g.g / n); s = -step q; x += s   (optimizers.py:100-102, 67-69)
-__global__ void lbfgs_cold_step(LbfgsDev* st, float* __restrict__ S, const float* __restrict__ g,
+template <int V>
+__global__ void lbfgs_cold_step(LbfgsDev* st_, float* __restrict__ S, const float* __restrict__ g,
                                 float* __restrict__ x, long long n, int slots, float step) {
-  if (st->count != 0) return;
-  const float scale = (float)sqrt(st->acc1[0] / (double)n);
-  float* s_new = S + (long long)(st->head % slots) * n;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-       k += (long long)gridDim.x * blockDim.x) {
-    float qv = g[k] / scale;
-    float sv = -step * qv;
-    s_new[k] = sv;
-    x[k] += sv;
+  if (st_->count != 0) return;
+  const float scale = (float)sqrt(st_->acc1[0] / (double)n);
+  float* s_new = S + (long long)(st_->head % slots) * n;
+  ST2_PACK_LOOP(k, n / V) {
+    const Pack<V> gv = ld<V>(g, k);
+    Pack<V> xv = ld<V>(x, k), sv;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float qv = gv.v[e] / scale;
+      sv.v[e] = -step * qv;
+      xv.v[e] += sv.v[e];
+    }
+    st<V>(s_new, k, sv);
+    st<V>(x, k, xv);
   }
 }
 
 // loop-2 step i.  i == 0 applies the H0 scaling gamma = s.y / y.y of the newest pair first.
-__global__ void lbfgs_loop2(LbfgsDev* st, float* __restrict__ S, const float* __restrict__ Y,
+template <int V>
+__global__ void lbfgs_loop2(LbfgsDev* st_, float* __restrict__ S, const float* __restrict__ Y,
                             float* __restrict__ q, float* __restrict__ x, long long n, int slots, int i,
                             float step) {
-  const int count = st->count;
+  const int count = st_->count;
   if (i >= count) return;
-  const int head = st->head;
+  const int head = st_->head;
   const int phys = (head + i) % slots;
   const int newest = (head + count - 1) % slots;
-  const float gamma = (float)(st->sy[newest] / st->yy[newest]);
-  double ydotq = (i == 0) ? st->acc_mid * (double)gamma : st->acc2[i];
-  const double beta = ydotq / st->sy[phys];
-  const float coef = (float)(st->alpha[i] - beta);
+  const float gamma = (float)(st_->sy[newest] / st_->yy[newest]);
+  const double ydotq = (i == 0) ? st_->acc_mid * (double)gamma : st_->acc2[i];
+  const double beta = ydotq / st_->sy[phys];
+  const float coef = (float)(st_->alpha[i] - beta);
   const float pre = (i == 0) ? gamma : 1.0f;
   const float* s = S + (long long)phys * n;
   const bool last = (i == count - 1);
-  const float* nxt = last ? nullptr : slot_ptr(Y, n, slots, head, i + 1);
+  const float* nxt = last ? s : slot_ptr(Y, n, slots, head, i + 1);
   float* s_new = S + (long long)((head + count) % slots) * n;
   float acc = 0.f;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-       k += (long long)gridDim.x * blockDim.x) {
-    float qv = q[k];
-    if (i == 0) qv *= pre;
-    qv = fmaf(coef, s[k], qv);
+  ST2_PACK_LOOP(k, n / V) {
+    Pack<V> qv = ld<V>(q, k);
+    const Pack<V> sv = ld<V>(s, k);
+#pragma unroll
+    for (int e = 0; e < V; ++e) qv.v[e] = fmaf(coef, sv.v[e], i == 0 ? qv.v[e] * pre : qv.v[e]);
     if (last) {
-      float sv = -step * qv;
-      s_new[k] = sv;
-      x[k] += sv;
+      Pack<V> xv = ld<V>(x, k), dv;
+#pragma unroll
+      for (int e = 0; e < V; ++e) { dv.v[e] = -step * qv.v[e]; xv.v[e] += dv.v[e]; }
+      st<V>(s_new, k, dv);
+      st<V>(x, k, xv);
     } else {
-      q[k] = qv;
-      acc += nxt[k] * qv;
+      const Pack<V> nv = ld<V>(nxt, k);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc = fmaf(nv.v[e], qv.v[e], acc);
+      st<V>(q, k, qv);
     }
   }
   if (!last) {
     float v[1] = {acc};
-    double* dst[1] = {&st->acc2[i + 1]};
+    double* dst[1] = {&st_->acc2[i + 1]};
     block_accumulate<1>(v, dst);
   }
 }
 
 // y = g_new - g_prev into the staging slot; s.y and y.y
-__global__ void lbfgs_make_pair(LbfgsDev* st, const float* __restrict__ S, float* __restrict__ Y,
+template <int V>
+__global__ void lbfgs_make_pair(LbfgsDev* st_, const float* __restrict__ S, float* __restrict__ Y,
                                 const float* __restrict__ g_new, const float* __restrict__ g_prev,
                                 long long n, int slots) {
-  const int phys = (st->head + st->count) % slots;
+  const int phys = (st_->head + st_->count) % slots;
   const float* s = S + (long long)phys * n;
   float* y = Y + (long long)phys * n;
   float a_sy = 0.f, a_yy = 0.f;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-       k += (long long)gridDim.x * blockDim.x) {
-    float yv = g_new[k] - g_prev[k];
-    y[k] = yv;
-    a_sy += s[k] * yv;
-    a_yy += yv * yv;
+  ST2_PACK_LOOP(k, n / V) {
+    const Pack<V> a = ld<V>(g_new, k), b = ld<V>(g_prev, k), sv = ld<V>(s, k);
+    Pack<V> yv;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      yv.v[e] = a.v[e] - b.v[e];
+      a_sy = fmaf(sv.v[e], yv.v[e], a_sy);
+      a_yy = fmaf(yv.v[e], yv.v[e], a_yy);
+    }
+    st<V>(y, k, yv);
   }
   float v[2] = {a_sy, a_yy};
-  double* dst[2] = {&st->acc_sy, &st->acc_yy};
+  double* dst[2] = {&st_->acc_sy, &st_->acc_yy};
   block_accumulate<2>(v, dst);
 }
 
@@ -270,17 +311,21 @@ int st2_lbfgs_advance(st2_lbfgs* o, float* x, const float* g, float step) {
   ProfScope ps(ctx, 7);
   lbfgs_clear_acc<<<1, 32, 0, s>>>(o->st);
   ST2_LAUNCH_CHECK(ctx);
-  lbfgs_first_dot<<<grid, kThreads, 0, s>>>(o->st, o->S, g, o->n, o->slots);
+  if (o->n % 4 == 0) lbfgs_first_dot<4><<<grid, kThreads, 0, s>>>(o->st, o->S, g, o->n, o->slots);
+  else lbfgs_first_dot<1><<<grid, kThreads, 0, s>>>(o->st, o->S, g, o->n, o->slots);
   ST2_LAUNCH_CHECK(ctx);
   for (int j = 0; j < o->count_ub; ++j) {
-    lbfgs_loop1<<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, g, o->q, o->n, o->slots, j);
+    if (o->n % 4 == 0) lbfgs_loop1<4><<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, g, o->q, o->n, o->slots, j);
+    else lbfgs_loop1<1><<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, g, o->q, o->n, o->slots, j);
     ST2_LAUNCH_CHECK(ctx);
   }
   // count may be 0 on the device even when the host bound is > 0 (all pairs rejected)
-  lbfgs_cold_step<<<grid, kThreads, 0, s>>>(o->st, o->S, g, x, o->n, o->slots, step);
+  if (o->n % 4 == 0) lbfgs_cold_step<4><<<grid, kThreads, 0, s>>>(o->st, o->S, g, x, o->n, o->slots, step);
+  else lbfgs_cold_step<1><<<grid, kThreads, 0, s>>>(o->st, o->S, g, x, o->n, o->slots, step);
   ST2_LAUNCH_CHECK(ctx);
   for (int i = 0; i < o->count_ub; ++i) {
-    lbfgs_loop2<<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, o->q, x, o->n, o->slots, i, step);
+    if (o->n % 4 == 0) lbfgs_loop2<4><<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, o->q, x, o->n, o->slots, i, step);
+    else lbfgs_loop2<1><<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, o->q, x, o->n, o->slots, i, step);
     ST2_LAUNCH_CHECK(ctx);
   }
   return 0;
@@ -292,7 +337,8 @@ int st2_lbfgs_commit(st2_lbfgs* o, const float* g_new, const float* g_prev) {
   cudaStream_t s = ctx->stream;
   const int grid = grid_for(o->n, ctx->sm_count);
   ProfScope ps(ctx, 7);
-  lbfgs_make_pair<<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, g_new, g_prev, o->n, o->slots);
+  if (o->n % 4 == 0) lbfgs_make_pair<4><<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, g_new, g_prev, o->n, o->slots);
+  else lbfgs_make_pair<1><<<grid, kThreads, 0, s>>>(o->st, o->S, o->Y, g_new, g_prev, o->n, o->slots);
   ST2_LAUNCH_CHECK(ctx);
   lbfgs_accept<<<1, 1, 0, s>>>(o->st, o->slots, o->n_corr);
   ST2_LAUNCH_CHECK(ctx);
