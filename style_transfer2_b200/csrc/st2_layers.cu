@@ -15,74 +15,100 @@ inline int ew_grid(long long work_items, int sm_count) {
 }
 
 // =============================================================================== conv1_1 forward
-// Work item: 128 consecutive pixels of one row.  Thread = (pixel, 32 of the 64 couts): 27 inputs in
-// registers, weights read from shared memory as warp-broadcast float4, 64-byte (fp16) or 128-byte
-// (fp32) contiguous store per thread.  Grid-stride over work items so the 6.9 KB weight tile is
-// staged once per block.  FMA-bound: 1728 FMA per pixel.
+// Work item: 256 consecutive pixels of one row.  Thread = (2 pixels, 32 of the 64 couts): every
+// warp-broadcast float4 of weights read from shared memory feeds 8 FMAs (the kernel is bound by the
+// shared-memory pipe otherwise), 27 inputs per pixel in registers.  fp16 output is staged through
+// an XOR-swizzled shared tile so global stores are whole 128-byte lines; fp32 output is written
+// directly (128 contiguous bytes per thread).  1728 FMA per pixel.
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                       const float* __restrict__ bias, T* __restrict__ out, int H, int W) {
   __shared__ __align__(16) float sw[27 * 64];          // [tap][ci][co]
   __shared__ __align__(16) float sb[64];
-  __shared__ float sx[3][3][130];
+  __shared__ float sx[3][3][258];
+  __shared__ uint4 so[sizeof(T) == 2 ? 128 * 8 : 1];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  const int tiles_w = (W + 127) / 128;
+  const int tiles_w = (W + 255) / 256;
   const int items = H * tiles_w;
   const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int h = item / tiles_w;
-    const int w0 = (item - h * tiles_w) * 128;
+    const int w0 = (item - h * tiles_w) * 256;
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 3 * 130; i += blockDim.x) {
-      const int c = i / (3 * 130), r = (i / 130) % 3, col = i % 130;
+    for (int i = threadIdx.x; i < 3 * 3 * 258; i += blockDim.x) {
+      const int c = i / (3 * 258), r = (i / 258) % 3, col = i % 258;
       const int hh = h + r - 1, ww = w0 + col - 1;
       float v = 0.f;
       if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[((long long)c * H + hh) * W + ww]);
       sx[c][r][col] = v;
     }
     __syncthreads();
-    const int ww = w0 + px;
-    if (ww >= W) continue;
-    float acc[32];
+    float acc0[32], acc1[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = sb[half * 32 + j];
+    for (int j = 0; j < 32; ++j) acc0[j] = acc1[j] = sb[half * 32 + j];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s = 0; s < 3; ++s)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float v = sx[c][r][px + s];
+          const float v0 = sx[c][r][px + s], v1 = sx[c][r][px + 128 + s];
           const float4* wr = reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + c) * 64 + half * 32]);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 wv = wr[q];
-            acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+            acc0[4 * q + 0] = fmaf(v0, wv.x, acc0[4 * q + 0]);
+            acc0[4 * q + 1] = fmaf(v0, wv.y, acc0[4 * q + 1]);
+            acc0[4 * q + 2] = fmaf(v0, wv.z, acc0[4 * q + 2]);
+            acc0[4 * q + 3] = fmaf(v0, wv.w, acc0[4 * q + 3]);
+            acc1[4 * q + 0] = fmaf(v1, wv.x, acc1[4 * q + 0]);
+            acc1[4 * q + 1] = fmaf(v1, wv.y, acc1[4 * q + 1]);
+            acc1[4 * q + 2] = fmaf(v1, wv.z, acc1[4 * q + 2]);
+            acc1[4 * q + 3] = fmaf(v1, wv.w, acc1[4 * q + 3]);
           }
         }
-    T* o = out + ((long long)h * W + ww) * 64 + half * 32;
-    if (sizeof(T) == 2) {
-      uint4* op = reinterpret_cast<uint4*>(o);
+    if (sizeof(T) == 4) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        __half2* hp = reinterpret_cast<__half2*>(&u);
+      for (int k = 0; k < 2; ++k) {
+        const int ww = w0 + px + k * 128;
+        if (ww < W) {
+          const float* a = k ? acc1 : acc0;
+          float4* op = reinterpret_cast<float4*>(out + ((long long)h * W + ww) * 64 + half * 32);
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          hp[e] = __floats2half2_rn(fmaxf(acc[8 * q + 2 * e], 0.f), fmaxf(acc[8 * q + 2 * e + 1], 0.f));
-        op[q] = u;
+          for (int q = 0; q < 8; ++q)
+            op[q] = make_float4(fmaxf(a[4 * q], 0.f), fmaxf(a[4 * q + 1], 0.f), fmaxf(a[4 * q + 2], 0.f),
+                                fmaxf(a[4 * q + 3], 0.f));
+        }
       }
     } else {
-      float4* op = reinterpret_cast<float4*>(o);
+      // two rounds of 128 pixels through the 16 KB staging tile
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        op[q] = make_float4(fmaxf(acc[4 * q], 0.f), fmaxf(acc[4 * q + 1], 0.f), fmaxf(acc[4 * q + 2], 0.f),
-                            fmaxf(acc[4 * q + 3], 0.f));
+      for (int k = 0; k < 2; ++k) {
+        const float* a = k ? acc1 : acc0;
+        if (k) __syncthreads();
+        uint4* row = so + px * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          __half2* hp = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            hp[e] = __floats2half2_rn(fmaxf(a[8 * q + 2 * e], 0.f), fmaxf(a[8 * q + 2 * e + 1], 0.f));
+          row[(half * 4 + q) ^ (px & 7)] = u;
+        }
+        __syncthreads();
+        const int base_w = w0 + k * 128;
+        const int npx = min(128, W - base_w);
+        if (npx > 0) {
+          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)h * W + base_w) * 64);
+          for (int i = threadIdx.x; i < npx * 8; i += blockDim.x) {
+            const int pp = i >> 3, c = i & 7;
+            dst[i] = so[pp * 8 + (c ^ (pp & 7))];
+          }
+        }
+      }
     }
   }
 }
@@ -90,22 +116,32 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
 // =============================================================================== conv1_1 dgrad
 // gx[ci][h][w] = sum_{tap,co} g[h+1-r][w+1-s][co] * W[co][ci][r][s];  w_bwd = [tap'][co][ci] with
 // tap' already flipped so the kernel reads g at (h + r' - 1, w + s' - 1).
-// Eight lanes share a pixel, each owning 8 of the 64 channels: a warp's 16-byte loads cover four
-// whole 128-byte pixel rows (fully coalesced), the 8x3 weights of a lane's channel group come from
-// shared memory as float4, and the three outputs are reduced across the 8 lanes with shuffles.
+// A block owns an 8 x 16 pixel tile, one warp per row.  Eight lanes share a pixel, each owning 8 of
+// the 64 channels, so a warp's 16-byte loads cover four whole 128-byte pixel rows (coalesced, and
+// the 3 x 3 neighbourhood re-hits L1).  Each lane handles 4 pixels of the row per tap so that the
+// 24 weights it fetches from shared memory (bank-conflict-free padding) feed 96 FMAs -- the kernel
+// is bound by the L1/shared pipe otherwise.  Outputs are reduced over the 8 lanes with shuffles.
 template <typename T> struct Load8 {};
 template <> struct Load8<__half> {
-  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  typedef uint4 raw_t;
+  static __device__ __forceinline__ raw_t load_raw(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void cvt(const raw_t& u, float (&v)[8]) {
     const __half2* hp = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hp[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
   }
 };
+struct Float8 { float4 a, b; };
 template <> struct Load8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  typedef Float8 raw_t;
+  static __device__ __forceinline__ raw_t load_raw(const float* p) {
+    raw_t r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+  }
+  static __device__ __forceinline__ void cvt(const raw_t& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
   }
 };
 
@@ -113,54 +149,86 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 conv_first_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int H,
                       int W) {
-  __shared__ __align__(16) float sw[9][8][24];          // [tap][channel group][8 co x 3 ci]
+  __shared__ __align__(16) float sw[9][8][28];          // [tap][channel group][8 co x 3 ci (+4 pad)]
   for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) {
     const int ci = i % 3, co = (i / 3) % 64, tap = i / 192;
     sw[tap][co >> 3][(co & 7) * 3 + ci] = w[i];
   }
   __syncthreads();
   const long long HW = (long long)H * W;
-  const int sub = threadIdx.x >> 3, cgp = threadIdx.x & 7;       // 32 pixels per block pass
-  const long long stride = (long long)gridDim.x * 32;
-  for (long long base = (long long)blockIdx.x * 32; base < HW; base += stride) {   // block-uniform trip count
-    const long long p = base + sub;
-    const bool live = p < HW;
-    const int h = live ? (int)(p / W) : 0, ww = live ? (int)(p - (long long)h * W) : 0;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (live) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 3, cgp = lane & 7;
+  const int tiles_w = (W + 15) / 16, tiles_h = (H + 7) / 8;
+  const long long n_tiles = (long long)tiles_w * tiles_h;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int th = (int)(tile / tiles_w), tw = (int)(tile - (long long)th * tiles_w);
+    const int h = th * 8 + warp;                       // warp-uniform
+    const int wbase = tw * 16 + sub;                   // this lane's pixels: wbase + 4 j
+    float acc[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
+    if (h < H) {
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int hh = h + r - 1;
-        if (hh < 0 || hh >= H) continue;
+        if (hh < 0 || hh >= H) continue;               // warp-uniform
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const int wc = ww + s - 1;
-          if (wc < 0 || wc >= W) continue;
-          float v[8];
-          Load8<T>::load(g + ((long long)hh * W + wc) * 64 + cgp * 8, v);
-          const float4* wr = reinterpret_cast<const float4*>(&sw[r * 3 + s][cgp][0]);
+          typename Load8<T>::raw_t raw[4];
+          bool ok[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int wc = wbase + 4 * j + s - 1;
+            ok[j] = wc >= 0 && wc < W;
+            const int wcl = min(max(wc, 0), W - 1);
+            raw[j] = Load8<T>::load_raw(g + ((long long)hh * W + wcl) * 64 + cgp * 8);
+          }
           float wv[24];
+          const float4* wr = reinterpret_cast<const float4*>(&sw[r * 3 + s][cgp][0]);
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
             const float4 t4 = wr[q];
             wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            a0 = fmaf(v[e], wv[3 * e + 0], a0);
-            a1 = fmaf(v[e], wv[3 * e + 1], a1);
-            a2 = fmaf(v[e], wv[3 * e + 2], a2);
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+            Load8<T>::cvt(raw[j], v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float ve = ok[j] ? v[e] : 0.f;
+              acc[j][0] = fmaf(ve, wv[3 * e + 0], acc[j][0]);
+              acc[j][1] = fmaf(ve, wv[3 * e + 1], acc[j][1]);
+              acc[j][2] = fmaf(ve, wv[3 * e + 2], acc[j][2]);
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float a = acc[j][c];
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        acc[j][c] = a;
+      }
+    if (h < H && cgp < 4) {
+      // lane cgp of each 8-lane group writes pixel j = cgp (select without dynamic register indexing)
+      float o0 = acc[0][0], o1 = acc[0][1], o2 = acc[0][2];
+      if (cgp == 1) { o0 = acc[1][0]; o1 = acc[1][1]; o2 = acc[1][2]; }
+      if (cgp == 2) { o0 = acc[2][0]; o1 = acc[2][1]; o2 = acc[2][2]; }
+      if (cgp == 3) { o0 = acc[3][0]; o1 = acc[3][1]; o2 = acc[3][2]; }
+      const int wo = wbase + 4 * cgp;
+      if (wo < W) {
+        const long long p = (long long)h * W + wo;
+        gx[p] = o0;
+        gx[HW + p] = o1;
+        gx[2 * HW + p] = o2;
+      }
     }
-    if (live && cgp < 3) gx[(long long)cgp * HW + p] = cgp == 0 ? a0 : (cgp == 1 ? a1 : a2);
   }
 }
 
@@ -492,8 +560,8 @@ __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restric
 template <typename T>
 int launch_conv_first_fwd(st2_ctx* ctx, const float* x, const float* w, const float* bias, T* out, int H,
                           int W) {
-  const int items = H * ((W + 127) / 128);
-  const int blocks = items < ctx->sm_count * 4 ? items : ctx->sm_count * 4;
+  const int items = H * ((W + 255) / 256);
+  const int blocks = items < ctx->sm_count * 2 ? items : ctx->sm_count * 2;
   conv_first_fwd_kernel<T><<<blocks, 256, 0, ctx->stream>>>(x, w, bias, out, H, W);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
@@ -504,7 +572,7 @@ template int launch_conv_first_fwd<__half>(st2_ctx*, const float*, const float*,
 template <typename T>
 int launch_conv_first_bwd(st2_ctx* ctx, const T* g, const float* w, float* gx, int H, int W) {
   const long long hw = (long long)H * W;
-  long long blocks = (hw + 31) / 32;
+  long long blocks = (long long)((W + 15) / 16) * ((H + 7) / 8);
   if (blocks > (long long)ctx->sm_count * 8) blocks = (long long)ctx->sm_count * 8;
   conv_first_bwd_kernel<T><<<(int)blocks, 256, 0, ctx->stream>>>(g, w, gx, H, W);
   ST2_LAUNCH_CHECK(ctx);
