@@ -79,6 +79,13 @@ long long st2_launch_count(st2_ctx* ctx);       /* kernels launched so far throu
 #define ST2_PROF_CATS 12
 int st2_profile(st2_ctx* ctx, int enable);
 int st2_profile_read(st2_ctx* ctx, double* ms_out, long long* count_out);
+/* measurement helpers: st2_debug_flags switches parts of the tcgen05 conv kernel off (timing
+ * experiments only: 1 no epilogue stores, 2 no MMA, 4 no A loads, 8 no B loads; results are then
+ * wrong by design).  st2_bench_layer times `reps` back-to-back launches of the conv producing
+ * `blob` (direction 0) or of the data-gradient conv consuming its gradient (direction 1) with CUDA
+ * events on the launch stream and returns the mean milliseconds per launch (SYNCHRONISES). */
+int st2_debug_flags(st2_ctx* ctx, int flags);
+int st2_bench_layer(st2_plan* plan, int blob, int direction, int reps, float* ms_out);
 /* conv weights in Caffe blob layout: w = (Cout, Cin, 3, 3) fp32, b = (Cout) fp32, host memory.
  * conv_index follows prototxt order (0 = conv1_1 ... 15 = conv5_4). */
 int st2_set_conv_weights(st2_ctx* ctx, int conv_index, const float* w_host, const float* b_host,

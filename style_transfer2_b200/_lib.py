@@ -37,6 +37,8 @@ _SIGS = {
     'st2_launch_count': (_ll, [_vp]),
     'st2_profile': (_i, [_vp, _i]),
     'st2_profile_read': (_i, [_vp, _dp, C.POINTER(C.c_longlong)]),
+    'st2_debug_flags': (_i, [_vp, _i]),
+    'st2_bench_layer': (_i, [_vp, _i, _i, _i, C.POINTER(C.c_float)]),
     'st2_set_conv_weights': (_i, [_vp, _i, _vp, _vp, _i, _i]),
     'st2_blob_count': (_i, []),
     'st2_blob_name': (C.c_char_p, [_i]),

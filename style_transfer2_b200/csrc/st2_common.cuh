@@ -51,6 +51,7 @@ struct st2_ctx {
   __half* wh_bwd[ST2_NUM_CONVS] = {};
   void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled entry point
   long long launches = 0;          // kernels launched through this context
+  int debug_flags = 0;             // timing experiments only (st2_debug_flags)
   // optional per-category device timing (CUDA events on the launch stream), see st2_profile()
   bool prof_on = false;
   struct ProfSpan { int cat; cudaEvent_t a, b; };

@@ -18,6 +18,8 @@
 #include "st2_kernels.h"
 #include "st2_tc.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int BM = 128;          // pixels per tile
@@ -26,10 +28,16 @@ constexpr int kNumThreads = 256;
 constexpr int kEpiWarp0 = 4;
 
 template <int BN> struct Cfg {
-  static constexpr int kABytes = BM * BK * 2;                 // 16 KB
-  static constexpr int kBBytes = BN * BK * 2;
+  // One pipeline stage carries KB consecutive 64-wide K blocks: the barrier hand-shake of a stage
+  // costs ~450 cycles of issue latency, so a stage must hold >= that much MMA work (2*BN cycles
+  // per K block at M = 128).
+  static constexpr int KB = (BN == 256) ? 1 : (BN == 128 ? 2 : 3);
+  static constexpr int kABlock = BM * BK * 2;                 // 16 KB per K block
+  static constexpr int kBBlock = BN * BK * 2;
+  static constexpr int kABytes = KB * kABlock;                // per stage
+  static constexpr int kBBytes = KB * kBBlock;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 4 : 3;         // 192 KB / 192 KB / 216 KB
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -37,6 +45,27 @@ template <int BN> struct Cfg {
 struct ConvGeom {
   int H, W, cin, cout, taps;
   int TH, TW, tiles_h, tiles_w, n_blocks, total_tiles, k_iters, cblocks;
+  int step_nb, step_tw, step_th;   // decomposition of gridDim.x in (n block, tile column, tile row) digits
+  int dbg;   // st2_debug_flags(): 1 no epilogue stores, 2 no MMA, 4 no A loads, 8 no B loads (timing experiments)
+};
+
+// Tile coordinates advanced by gridDim.x per step without divisions (mixed-radix add with carry).
+struct TileWalk {
+  int nb, tw, th;
+  __device__ __forceinline__ void init(const ConvGeom& g, int tile) {
+    nb = tile % g.n_blocks;
+    const int pt = tile / g.n_blocks;
+    tw = pt % g.tiles_w;
+    th = pt / g.tiles_w;
+  }
+  __device__ __forceinline__ void next(const ConvGeom& g) {
+    nb += g.step_nb;
+    if (nb >= g.n_blocks) { nb -= g.n_blocks; ++tw; }
+    tw += g.step_tw;
+    if (tw >= g.tiles_w) { tw -= g.tiles_w; ++th; }
+    if (tw >= g.tiles_w) { tw -= g.tiles_w; ++th; }
+    th += g.step_th;
+  }
 };
 
 template <int BN>
@@ -65,7 +94,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
     tc::fence_mbar_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, C::kTmemCols);
@@ -76,48 +105,83 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const int nb = tile % g.n_blocks, pt = tile / g.n_blocks;
-        const int h0 = (pt / g.tiles_w) * g.TH, w0 = (pt % g.tiles_w) * g.TW;
-        for (int it = 0; it < g.k_iters; ++it) {
-          const int tap = it / g.cblocks, cb = it - tap * g.cblocks;
-          const int dh = (g.taps == 9) ? tap / 3 - 1 : 0;
-          const int dw = (g.taps == 9) ? tap % 3 - 1 : 0;
-          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-          tc::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          tc::tma_load_3d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], cb * BK, w0 + dw, h0 + dh);
-          tc::tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], tap * g.cin + cb * BK, nb * BN);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+    // whole warp runs the (uniform) loop; one elected lane issues expect_tx + the TMA loads of a stage
+    int stage = 0; uint32_t phase = 0;
+    const bool three = (g.taps == 9);
+    TileWalk tk;
+    tk.init(g, blockIdx.x);
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, tk.next(g)) {
+      const int nb = tk.nb;
+      const int h0 = tk.th * g.TH, w0 = tk.tw * g.TW;
+      int tap = 0, cb = 0;                               // K block index it = tap * cblocks + cb
+      for (int it = 0; it < g.k_iters; it += C::KB) {
+        const int nkb = (g.k_iters - it < C::KB) ? g.k_iters - it : C::KB;
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (tc::elect_one()) {
+          uint32_t bytes = (uint32_t)nkb * (C::kABlock + C::kBBlock);
+          if (g.dbg & 4) bytes -= (uint32_t)nkb * C::kABlock;
+          if (g.dbg & 8) bytes -= (uint32_t)nkb * C::kBBlock;
+          if (bytes) tc::mbar_expect_tx(&full_bar[stage], bytes); else tc::mbar_arrive(&full_bar[stage]);
         }
+#pragma unroll
+        for (int j = 0; j < C::KB; ++j) {
+          if (j < nkb) {
+            const int dh = three ? tap / 3 - 1 : 0;
+            const int dw = three ? tap % 3 - 1 : 0;
+            if (tc::elect_one()) {
+              if (!(g.dbg & 4))
+                tc::tma_load_3d(smem_a + stage * C::kABytes + j * C::kABlock, &tmap_a, &full_bar[stage], cb * BK,
+                                w0 + dw, h0 + dh);
+              if (!(g.dbg & 8))
+                tc::tma_load_2d(smem_b + stage * C::kBBytes + j * C::kBBlock, &tmap_b, &full_bar[stage],
+                                tap * g.cin + cb * BK, nb * BN);
+            }
+            if (++cb == g.cblocks) { cb = 0; ++tap; }
+          }
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_f16(BM, BN, 0, 0);
-      int stage = 0; uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = tc::idesc_f16(BM, BN, 0, 0);
+    const uint64_t a_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_a));
+    const uint64_t b_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_b));
+    int stage = 0; uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int it = 0; it < g.k_iters; it += C::KB) {
+        const int nkb = (g.k_iters - it < C::KB) ? g.k_iters - it : C::KB;
+        tc::mbar_wait(&full_bar[stage], phase);
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int it = 0; it < g.k_iters; ++it) {
-          tc::mbar_wait(&full_bar[stage], phase);
-          tc::fence_after_sync();
-          const uint64_t a_desc = tc::smem_desc_k_sw128(tc::smem_u32(smem_a + stage * C::kABytes));
-          const uint64_t b_desc = tc::smem_desc_k_sw128(tc::smem_u32(smem_b + stage * C::kBBytes));
+        if (tc::elect_one()) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (C::kABytes >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (C::kBBytes >> 4));
+          if (!(g.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)            // +32 bytes (>>4 = 2) per 16-element K step
-            tc::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it | k) != 0);
-          tc::umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            for (int j = 0; j < C::KB; ++j) {
+              if (j < nkb) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)        // +32 bytes (>>4 = 2) per 16-element K step
+                  tc::umma_f16(d_tmem, a_desc + (uint64_t)(j * (C::kABlock >> 4) + 2 * k),
+                               b_desc + (uint64_t)(j * (C::kBBlock >> 4) + 2 * k), idesc, (it | j | k) != 0);
+              }
+            }
+          }
+          if (g.dbg & 16) tc::mbar_arrive(&empty_bar[stage]);   // experiment: plain arrive instead of commit
+          else tc::umma_commit(&empty_bar[stage]);     // frees the smem slot when the MMAs retire
         }
-        tc::umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
     // ================================ epilogue ====================================
@@ -125,15 +189,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row = ew * 32 + lane;                    // pixel index inside the tile
     float ss = 0.f;
     int local = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local) {
+    const int row_h = row / g.TW, row_w = row % g.TW;
+    TileWalk tk;
+    tk.init(g, blockIdx.x);
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local, tk.next(g)) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int nb = tile % g.n_blocks, pt = tile / g.n_blocks;
-      const int h = (pt / g.tiles_w) * g.TH + row / g.TW;
-      const int w = (pt % g.tiles_w) * g.TW + row % g.TW;
-      const bool valid = (h < g.H) && (w < g.W);
+      const int nb = tk.nb;
+      const int h = tk.th * g.TH + row_h;
+      const int w = tk.tw * g.TW + row_w;
+      const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
-      tc::mbar_wait(&tmem_full[acc], acc_phase);
+      if (lane == 0) tc::mbar_wait(&tmem_full[acc], acc_phase);     // one poller per warp
+      __syncwarp();
       tc::fence_after_sync();
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
@@ -188,7 +256,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       tc::fence_before_sync();
-      tc::mbar_arrive(&tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
     }
     if (sumsq != nullptr) {
       const double tot = warp_sum_d((double)ss);
@@ -254,7 +323,27 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   g.TH = BM / g.TW;
   g.tiles_h = (H + g.TH - 1) / g.TH;
   g.tiles_w = (W + g.TW - 1) / g.TW;
-  p->bn = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  // Pick the N tile: time ~ waves * K blocks * max(MMA cycles, hand-shake cycles / K blocks per stage).
+  // Narrower tiles cost more operand traffic per flop but quantise better over the 148 SMs.
+  {
+    const int cand[3] = {256, 128, 64};
+    const int kb[3] = {1, 2, 3};
+    double best = 1e30;
+    p->bn = 64;
+    const char* force = getenv("ST2_TC_BN");
+    for (int c = 0; c < 3; ++c) {
+      const int bn = cand[c];
+      if (cout % bn) continue;
+      if (force && atoi(force) == bn) { p->bn = bn; best = -1; break; }
+      const long long tiles = (long long)g.tiles_h * g.tiles_w * (cout / bn);
+      const long long waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
+      const double eff = bn == 256 ? 1.0 : (bn == 128 ? 1.30 : 1.8);   // shared-memory operand traffic per flop
+      const double per_kblock = 2.0 * bn * eff > 450.0 / kb[c] ? 2.0 * bn * eff : 450.0 / kb[c];
+      const double epi = 300.0 + 1.5 * bn;                       // drain of one tile when it is not hidden
+      const double cost = (double)waves * ((double)taps * (cin / BK) * per_kblock + epi);
+      if (cost < best * 0.97) { best = cost; p->bn = bn; }       // prefer the wider tile on near-ties
+    }
+  }
   g.n_blocks = cout / p->bn;
   g.total_tiles = g.tiles_h * g.tiles_w * g.n_blocks;
   g.cblocks = cin / BK;
@@ -289,6 +378,10 @@ static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
     attr_set = true;
   }
   const int grid = p->g.total_tiles < ctx->sm_count ? p->g.total_tiles : ctx->sm_count;
+  p->g.dbg = ctx->debug_flags;
+  p->g.step_nb = grid % p->g.n_blocks;
+  p->g.step_tw = (grid / p->g.n_blocks) % p->g.tiles_w;
+  p->g.step_th = (grid / p->g.n_blocks) / p->g.tiles_w;
   tc_conv_kernel<BN><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias,
                                                                               act, out, epi, out_scale, sumsq);
   ST2_LAUNCH_CHECK(ctx);

@@ -70,11 +70,11 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramGeom g, float
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        const int p = (int)(p_begin + (long long)it * KP);
-        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < k_iters; ++it) {
+      const int p = (int)(p_begin + (long long)it * KP);
+      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -85,16 +85,17 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramGeom g, float
 #pragma unroll
         for (int b = 0; b < GN / 64; ++b)
           tc::tma_load_2d(smem_b + stage * C::kBBytes + b * kBoxBytes, &tmap, &full_bar[stage], n0 + b * 64, p);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == C::kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_f16(GM, GN, 1, 1);      // both operands MN-major
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        tc::mbar_wait(&full_bar[stage], phase);
-        tc::fence_after_sync();
+    constexpr uint32_t idesc = tc::idesc_f16(GM, GN, 1, 1);      // both operands MN-major
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < k_iters; ++it) {
+      tc::mbar_wait(&full_bar[stage], phase);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
         const uint32_t a_addr = tc::smem_u32(smem_a + stage * C::kABytes);
         const uint32_t b_addr = tc::smem_u32(smem_b + stage * C::kBBytes);
 #pragma unroll
@@ -104,14 +105,17 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramGeom g, float
           tc::umma_f16(tmem_base, a_desc, b_desc, idesc, (it | k) != 0);
         }
         tc::umma_commit(&empty_bar[stage]);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
-      tc::umma_commit(done_bar);
+      __syncwarp();
+      if (++stage == C::kStages) { stage = 0; phase ^= 1; }
     }
+    if (tc::elect_one()) tc::umma_commit(done_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int i = m0 + ew * 32 + lane;
-    tc::mbar_wait(done_bar, 0);
+    if (lane == 0) tc::mbar_wait(done_bar, 0);
+    __syncwarp();
     tc::fence_after_sync();
     const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16);
     float* dst = partials + ((long long)split * g.C + i) * g.C + n0;

@@ -481,6 +481,12 @@ int st2_set_stream(st2_ctx* ctx, void* s) {
 
 long long st2_launch_count(st2_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int st2_debug_flags(st2_ctx* ctx, int flags) {
+  if (!ctx) return ST2_ERR_ARG;
+  ctx->debug_flags = flags;
+  return 0;
+}
+
 int st2_profile(st2_ctx* ctx, int enable) {
   if (!ctx) return ST2_ERR_ARG;
   ctx->prof_on = enable != 0;
@@ -599,6 +605,42 @@ int st2_plan_blob_dims(st2_plan* pl, int blob, int* c, int* h, int* w) {
 int st2_forward(st2_plan* pl, const float* x, int top) {
   if (!pl || !x || top < 0 || top >= ST2_NUM_BLOBS) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_forward: bad arguments");
   return pl->prec == ST2_PREC_FP16 ? forward_impl<__half>(pl, x, top) : forward_impl<float>(pl, x, top);
+}
+
+int st2_bench_layer(st2_plan* pl, int blob, int direction, int reps, float* ms_out) {
+  if (!pl || !ms_out || blob < 2 || blob >= ST2_NUM_BLOBS || reps < 1 || g_blobs[blob].kind != KIND_CONV)
+    return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_bench_layer: needs a conv blob above conv1_1");
+  st2_ctx* ctx = pl->ctx;
+  Blob& cur = pl->b[blob];
+  Blob& below = pl->b[blob - 1];
+  const int ci = g_blobs[blob].conv_index;
+  cudaEvent_t e0, e1;
+  ST2_CUDA(ctx, cudaEventCreate(&e0));
+  ST2_CUDA(ctx, cudaEventCreate(&e1));
+  int rc = 0;
+  for (int it = -2; it < reps && !rc; ++it) {
+    if (it == 0) ST2_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    if (pl->prec == ST2_PREC_FP16) {
+      rc = direction == 0
+               ? tc_conv_launch(ctx, cur.tc_fwd, ctx->bias[ci], nullptr, (__half*)cur.act, EPI_BIAS_RELU, 1.f, nullptr)
+               : tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad, EPI_MASK, 1.f, nullptr);
+    } else {
+      rc = direction == 0
+               ? launch_conv_exact(ctx, (const float*)below.act, ctx->wf32_fwd[ci], ctx->bias[ci], nullptr,
+                                   (float*)cur.act, cur.H, cur.W, below.C, cur.C, EPI_BIAS_RELU)
+               : launch_conv_exact(ctx, (const float*)cur.grad, ctx->wf32_bwd[ci], nullptr, (const float*)below.act,
+                                   (float*)below.grad, cur.H, cur.W, cur.C, below.C, EPI_MASK);
+    }
+  }
+  if (rc) return rc;
+  ST2_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  ST2_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  ST2_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / reps;
+  return 0;
 }
 
 int st2_blob_export(st2_plan* pl, int blob, float* out) {

@@ -34,12 +34,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware until
+      : "memory");                                          // the phase completes instead of re-polling
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU.
@@ -51,6 +51,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// One lane of a converged warp (elect.sync): issuing the single-thread instructions (TMA, tcgen05.mma,
+// tcgen05.commit) under this predicate keeps the surrounding loop warp-uniform, so ptxas computes
+// descriptors / coordinates in the uniform datapath instead of wrapping every issue in an
+// ELECT / R2UR / BRA.U.ANY loop (which made one k-iteration cost ~500 cycles of issue latency).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- TMA ---------------------------------------------------------------------------------------
