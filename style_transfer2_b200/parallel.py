@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing for the two ways the path shards.
+
+* Independent jobs (serving, BASELINE config 5): jobs are assigned to ranks round-robin; every rank
+  runs its jobs on its own GPU with no data-path collective.  ``torch.distributed`` (NCCL on GPUs,
+  gloo in CPU tests) is used only for barriers, the max-over-ranks timing and gathering small results.
+* One large canvas split in row strips with halo exchange + Gram / dot-product all-reduce
+  (config 4) is not built yet; ``strip_bounds`` fixes the partition it will use.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_jobs(n_jobs, world_size, rank):
+    """Indices of the jobs rank ``rank`` runs (round-robin: job j -> rank j % world_size)."""
+    if not 0 <= rank < world_size:
+        raise ValueError('rank %d outside world of %d' % (rank, world_size))
+    return list(range(rank, n_jobs, world_size))
+
+
+def strip_bounds(height, world_size, align=16):
+    """Row strips for spatial tiling: boundaries at multiples of ``align`` (16 rows keep all five
+    2x2/2 ceil-mode pools aligned), sizes as equal as that allows.  Returns [(row0, row1)] per rank;
+    trailing ranks may get empty strips on tiny canvases."""
+    blocks = (height + align - 1) // align
+    out, start = [], 0
+    for r in range(world_size):
+        nb = blocks // world_size + (1 if r < blocks % world_size else 0)
+        end = min(height, start + nb * align)
+        out.append((start, end))
+        start = end
+    return out
+
+
+def all_max(value, device=None):
+    """Max of a Python float over all ranks (device-timed milliseconds -> slowest rank)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def all_sum(value, device=None):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_objects(obj):
+    """List of every rank's picklable ``obj`` on every rank (per-job results of a serving run)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def run_jobs(jobs, step_fn, world_size=1, rank=0):
+    """Run ``step_fn(job_index, job)`` for this rank's share of ``jobs``; returns {index: result}."""
+    return {j: step_fn(j, jobs[j]) for j in shard_jobs(len(jobs), world_size, rank)}

@@ -1,0 +1,94 @@
+"""Wire-protocol conformance of the drop-in worker on a GPU: a scripted stand-in for app.py talks to
+``Worker`` over real ZeroMQ PUSH/PULL sockets with pickled ``messages.*`` (worker.py:318-409,
+app.py:244-262,293-323 for the message sequences)."""
+import socket
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_worker_speaks_the_reference_protocol(golden):
+    zmq = pytest.importorskip('zmq')
+    from style_transfer2_b200 import messages as m
+    from style_transfer2_b200 import vgg
+    from style_transfer2_b200.worker import Worker
+    m.install_as_toplevel()
+    g = golden('small')
+    cfg = {'worker_socket': 'tcp://127.0.0.1:%d' % _port(), 'app_socket': 'tcp://127.0.0.1:%d' % _port(),
+           'gpu': '0', 'precision': 'fp16'}
+    ctx = zmq.Context.instance()
+    app_in = ctx.socket(zmq.PULL)
+    app_in.bind(cfg['app_socket'])
+    app_out = ctx.socket(zmq.PUSH)
+    app_out.connect(cfg['worker_socket'])
+    app_in.RCVTIMEO = 120000
+    errors = []
+
+    def serve():
+        try:
+            Worker(cfg).run()
+        except Exception as e:          # pragma: no cover
+            errors.append(e)
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    try:
+        ready = app_in.recv_pyobj()
+        assert isinstance(ready, m.WorkerReady) and ready.layers == vgg.BLOBS
+
+        app_out.send_pyobj(m.StartIteration())                       # nothing set yet
+        assert isinstance(app_in.recv_pyobj(), m.GetImages)
+
+        weights = {'content': {'conv4_2': 0.08}, 'style': {'conv1_1': 1, 'conv2_1': 1, 'conv3_1': 1, 'conv4_1': 1},
+                   'deepdream': {}}
+        params = {'p': 50, 'p_power': 6, 'tv': 5, 'tv_power': 2}
+        app_out.send_pyobj(m.SetWeights(weights, params))
+        app_out.send_pyobj(m.SetOptimizer('lbfgs'))
+        app_out.send_pyobj(m.SetImages(size=g['x0'].shape[:2], input_image=g['x0'], content_image=g['content'],
+                                       style_image=g['style'], reset_state=True))
+        app_out.send_pyobj(m.StartIteration())
+        seen = []
+        for _ in range(3):
+            it = app_in.recv_pyobj()
+            assert isinstance(it, m.Iterate)
+            img = np.float32(it.image)
+            assert img.shape == g['x0'].shape and np.isfinite(img).all()
+            assert 'loss' in it.trace and it.trace['fevals'] == it.i
+            assert all(isinstance(v, (int, float)) for v in it.trace.values())
+            seen.append(it.i)
+        assert seen == [1, 2, 3]
+
+        app_out.send_pyobj(object())                                   # unknown message: logged, ignored
+        app_out.send_pyobj(m.PauseIteration())
+        app_out.send_pyobj(m.SetOptimizer('adam'))                     # class change -> reset, i restarts
+        h, w = g['x0'].shape[:2]
+        app_out.send_pyobj(m.SetImages(size=(h + 8, w + 8), input_image=m.SetImages.RESAMPLE,
+                                       content_image=m.SetImages.RESAMPLE))
+        app_out.send_pyobj(m.StartIteration())
+        while True:
+            it = app_in.recv_pyobj()
+            if isinstance(it, m.Iterate) and np.float32(it.image).shape == (h + 8, w + 8, 3):
+                break
+        assert it.i >= 1 and np.isfinite(it.trace['loss'])
+
+        app_out.send_pyobj(m.Shutdown())
+        while True:
+            last = app_in.recv_pyobj()
+            if isinstance(last, m.Shutdown):
+                break
+        th.join(30)
+        assert not th.is_alive() and not errors
+    finally:
+        app_in.close(0)
+        app_out.close(0)
