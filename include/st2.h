@@ -167,6 +167,18 @@ int st2_lbfgs_reset(st2_lbfgs* opt);                       /* objective_changed(
 int st2_lbfgs_advance(st2_lbfgs* opt, float* x_dev, const float* g_dev, float step_size);
 /* y = g_new - g_prev; keep (s, y) iff s.y > 1e-10; FIFO cap n_corr (optimizers.py:72-74,79-87) */
 int st2_lbfgs_commit(st2_lbfgs* opt, const float* g_new_dev, const float* g_prev_dev);
+/* The same two calls split around their cross-vector reductions, for callers that shard the vectors
+ * over several GPUs (row strips): after *_begin, all-reduce (sum) the st2_lbfgs_sums_count() doubles
+ * at st2_lbfgs_sums_dev(), then call *_end.  advance_begin only produces sums on the first step
+ * after a reset/load.  st2_lbfgs_set_global_length gives the un-sharded vector length (p.size in
+ * optimizers.py:102). */
+int st2_lbfgs_advance_begin(st2_lbfgs* opt, const float* g_dev);
+int st2_lbfgs_advance_end(st2_lbfgs* opt, float* x_dev, const float* g_dev, float step_size);
+int st2_lbfgs_commit_begin(st2_lbfgs* opt, const float* g_new_dev, const float* g_prev_dev);
+int st2_lbfgs_commit_end(st2_lbfgs* opt);
+double* st2_lbfgs_sums_dev(st2_lbfgs* opt);
+int st2_lbfgs_sums_count(void);
+int st2_lbfgs_set_global_length(st2_lbfgs* opt, double n_total);
 /* state transfer for teacher-forced tests: count pairs, oldest first; S, Y: count x n fp32 (dev) */
 int st2_lbfgs_load(st2_lbfgs* opt, int count, const float* s_dev, const float* y_dev,
                    const double* sy_host);

@@ -75,6 +75,13 @@ _SIGS = {
     'st2_lbfgs_reset': (_i, [_vp]),
     'st2_lbfgs_advance': (_i, [_vp, _vp, _vp, _f]),
     'st2_lbfgs_commit': (_i, [_vp, _vp, _vp]),
+    'st2_lbfgs_advance_begin': (_i, [_vp, _vp]),
+    'st2_lbfgs_advance_end': (_i, [_vp, _vp, _vp, _f]),
+    'st2_lbfgs_commit_begin': (_i, [_vp, _vp, _vp]),
+    'st2_lbfgs_commit_end': (_i, [_vp]),
+    'st2_lbfgs_sums_dev': (_vp, [_vp]),
+    'st2_lbfgs_sums_count': (_i, []),
+    'st2_lbfgs_set_global_length': (_i, [_vp, _d]),
     'st2_lbfgs_load': (_i, [_vp, _i, _vp, _vp, _dp]),
     'st2_lbfgs_export': (_i, [_vp, _ip, _vp, _vp, _dp]),
     'st2_adam_step': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _d, _d, _i, _i]),

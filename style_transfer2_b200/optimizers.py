@@ -85,6 +85,8 @@ class LBFGSOptimizer:
         self._ensure()
 
     def _ensure(self):
+        if self.x is None:                      # the reference builds optimizers before any image is set
+            return
         if self._h is not None and self._n == self.x.numel():
             return
         self._free()
@@ -103,6 +105,7 @@ class LBFGSOptimizer:
 
     def step(self):
         """optimizers.py:62-77."""
+        self._ensure()
         if self.loss is None:
             self.loss, self.grad = self.opfunc(self.x)
         self._call('st2_lbfgs_advance', _p(self.x), _p(self.grad), float(self.step_size))
@@ -122,7 +125,8 @@ class LBFGSOptimizer:
 
     def objective_changed(self):
         """optimizers.py:121-125."""
-        self._call('st2_lbfgs_reset')
+        if self._h is not None:
+            self._call('st2_lbfgs_reset')
         self.loss, self.grad = None, None
 
     # -- state access (teacher-forced parity tests, checkpointing)

@@ -38,8 +38,9 @@ def test_worker_speaks_the_reference_protocol(golden):
     def serve():
         try:
             Worker(cfg).run()
-        except Exception as e:          # pragma: no cover
-            errors.append(e)
+        except Exception:               # pragma: no cover
+            import traceback
+            errors.append(traceback.format_exc())
 
     th = threading.Thread(target=serve, daemon=True)
     th.start()
@@ -61,7 +62,7 @@ def test_worker_speaks_the_reference_protocol(golden):
         seen = []
         for _ in range(3):
             it = app_in.recv_pyobj()
-            assert isinstance(it, m.Iterate)
+            assert isinstance(it, m.Iterate), (it, errors)
             img = np.float32(it.image)
             assert img.shape == g['x0'].shape and np.isfinite(img).all()
             assert 'loss' in it.trace and it.trace['fevals'] == it.i
