@@ -59,6 +59,7 @@ extern "C" {
 #define ST2_G_T_GRAD 11
 #define ST2_G_P_GRAD 12
 #define ST2_G_GRAD 13
+#define ST2_G_HALO_TIMEOUT 14     /* row strips: 1.0 when a halo wait timed out (a neighbour died) */
 
 typedef struct st2_ctx st2_ctx;
 typedef struct st2_plan st2_plan;
@@ -134,6 +135,13 @@ int st2_set_norm(st2_plan* plan, int kind /*0 c,1 s,2 d*/, int blob, double valu
 /* opfunc: loss and (want_grad) gradient of the objective at x.  grad_dev: fp32 NCHW.  All
  * scalars (loss terms, RMS traces, norms) land in the plan's scalar block. */
 int st2_eval(st2_plan* plan, const float* x_dev, float* grad_dev, int want_grad);
+/* The same evaluation in four phases; st2_eval == begin, mid, end, final back to back.  On a row strip
+ * (below) the caller all-reduces (sum) st2_strip_reduce_block(which) across the strips after
+ * begin (which = 0), mid (1) and end (2).  grad_dev may be NULL when want_grad was 0. */
+int st2_eval_begin(st2_plan* plan, const float* x_dev, int want_grad);
+int st2_eval_mid(st2_plan* plan);
+int st2_eval_end(st2_plan* plan, float* grad_dev);
+int st2_eval_final(st2_plan* plan);
 /* read the scalar block (ST2_SCAL_TOTAL doubles) -- SYNCHRONISES the stream. */
 int st2_read_scalars(st2_plan* plan, double* host_out);
 /* enqueue a copy of the scalar block into PINNED host memory; no synchronisation (pair it with a
@@ -141,6 +149,28 @@ int st2_read_scalars(st2_plan* plan, double* host_out);
 int st2_copy_scalars_async(st2_plan* plan, double* pinned_host_out);
 /* device address of the scalar block (for callers that keep everything on the device) */
 double* st2_scalars_dev(st2_plan* plan);
+
+/* ---- row strips: one canvas split over several GPUs (new; the reference holds the whole image in one
+ * caffe.Net, worker.py:84-86, capped by max_size, app.py:183-185) --------------------------------
+ * A strip plan holds rows [row0, row1) of an H_total x W canvas plus one halo row on either side of
+ * every activation / gradient tensor.  Strips start at multiples of 16 rows.  x / grad / L-BFGS
+ * vectors of a strip are dense fp32 (3, row1-row0, W).  Neighbouring strips (circular: the TV term
+ * wraps around the canvas) are attached either through a CUDA IPC handle (one process per GPU; halo
+ * rows then travel as peer stores over NVLink) or directly when they live in the same process.
+ * st2_forward / st2_capture_content / st2_eval_* work on strip plans and must be called by all strips
+ * in the same order; st2_gram returns the strip's UN-normalised Gram sum; st2_eval (one shot) works
+ * only for world == 1; st2_backward is not available. */
+#define ST2_IPC_HANDLE_BYTES 64
+int st2_strip_plan_create(st2_ctx* ctx, int height_total, int width, int row0, int row1, int rank,
+                          int world, int precision, st2_plan** out);
+int st2_strip_ipc_handle(st2_plan* plan, void* handle_out /* ST2_IPC_HANDLE_BYTES */);
+/* side 0: the strip above (rank-1, or the last strip for rank 0), side 1: the strip below.  Exactly one of
+ * ipc_handle / local_peer is given.  peer_rows: the rows that strip holds. */
+int st2_strip_attach(st2_plan* plan, int side, const void* ipc_handle, st2_plan* local_peer, int peer_rows);
+/* which 0: Gram sums (fp32), 1: per-blob partial sums (f64), 2: six pixel-space sums (f64) */
+int st2_strip_reduce_block(st2_plan* plan, int which, void** dev_out, long long* count_out);
+/* 1 when a halo wait timed out since the plan was created -- SYNCHRONISES */
+int st2_strip_halo_error(st2_plan* plan, int* err_out);
 
 /* ---- pixel-space pieces, usable on their own -------------------------------------------------
  * utils.tv_norm / p_norm (utils.py:285-304) + gradient assembly (worker.py:295-297).

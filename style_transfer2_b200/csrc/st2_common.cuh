@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <initializer_list>
 #include <vector>
 
 #include "../../include/st2.h"
@@ -67,6 +68,16 @@ struct ProfScope {
 };
 
 int st2_fail(st2_ctx* ctx, int code, const char* fmt, ...);
+
+// Every kernel of the library is registered here and loaded when a context is created.  CUDA loads
+// kernels lazily on first launch and that load may wait for the device to go idle; strips that spin on a
+// neighbour's flag while the host is about to launch a not-yet-loaded kernel would deadlock
+// (CUDA programming guide, "Lazy Loading -> Concurrent execution").
+std::vector<const void*>& st2_kernel_registry();
+struct St2KernelReg {
+  St2KernelReg(std::initializer_list<const void*> fns) { for (const void* f : fns) st2_kernel_registry().push_back(f); }
+};
+#define ST2_KFN(...) reinterpret_cast<const void*>(&__VA_ARGS__)
 
 #define ST2_CUDA(ctx, expr)                                                             \
   do {                                                                                  \

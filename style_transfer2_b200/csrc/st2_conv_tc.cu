@@ -46,6 +46,7 @@ struct ConvGeom {
   int H, W, cin, cout, taps;
   int TH, TW, tiles_h, tiles_w, n_blocks, total_tiles, k_iters, cblocks;
   int step_nb, step_tw, step_th;   // decomposition of gridDim.x in (n block, tile column, tile row) digits
+  int hoff;  // row strips: the tensor map starts `hoff` halo rows above the first output row
   int dbg;   // st2_debug_flags(): 1 no epilogue stores, 2 no MMA, 4 no A loads, 8 no B loads (timing experiments)
 };
 
@@ -131,7 +132,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (tc::elect_one()) {
               if (!(g.dbg & 4))
                 tc::tma_load_3d(smem_a + stage * C::kABytes + j * C::kABlock, &tmap_a, &full_bar[stage], cb * BK,
-                                w0 + dw, h0 + dh);
+                                w0 + dw, h0 + dh + g.hoff);
               if (!(g.dbg & 8))
                 tc::tma_load_2d(smem_b + stage * C::kBBytes + j * C::kBBlock, &tmap_b, &full_bar[stage],
                                 tap * g.cin + cb * BK, nb * BN);
@@ -313,12 +314,13 @@ int st2_encode_tmap(st2_ctx* ctx, CUtensorMap* map, const void* base, int rank, 
 }
 
 int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, int H, int W, int cin, int cout,
-                        int taps, TcConvPlan** out) {
+                        int taps, TcConvPlan** out, int halo) {
   if (cin % 64 || cout % 64 || (taps != 9 && taps != 1))
     return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: cin/cout must be multiples of 64 (got %d/%d)", cin, cout);
   TcConvPlan* p = new TcConvPlan();
   ConvGeom& g = p->g;
   g.H = H; g.W = W; g.cin = cin; g.cout = cout; g.taps = taps;
+  g.hoff = halo;                 // `in` then points at the first halo row; H counts the output rows only
   g.TW = (W <= 4) ? 4 : (W <= 8 ? 8 : 16);
   g.TH = BM / g.TW;
   g.tiles_h = (H + g.TH - 1) / g.TH;
@@ -349,7 +351,7 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   g.cblocks = cin / BK;
   g.k_iters = taps * g.cblocks;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H};
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)(H + 2 * halo)};
     cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH};
     int rc = st2_encode_tmap(ctx, &p->tmap_a, in, 3, dims, strides, box);
@@ -398,3 +400,5 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     default:  return launch_bn<64>(ctx, p, bias, act, out, epi, out_scale, sumsq);
   }
 }
+
+static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>)});

@@ -254,3 +254,8 @@ int launch_feature_sums_v(st2_ctx* ctx, const T* act, const T* fc, long long n, 
 }
 template int launch_feature_sums_v<float>(st2_ctx*, const float*, const float*, long long, double*, double*);
 template int launch_feature_sums_v<__half>(st2_ctx*, const __half*, const __half*, long long, double*, double*);
+
+static St2KernelReg g_reg_elementwise({
+    ST2_KFN(pool_fwd_vec_kernel<float>), ST2_KFN(pool_fwd_vec_kernel<__half>), ST2_KFN(pool_bwd_vec_kernel<float>),
+    ST2_KFN(pool_bwd_vec_kernel<__half>), ST2_KFN(combine_vec_kernel<float>), ST2_KFN(combine_vec_kernel<__half>),
+    ST2_KFN(feature_sums_vec_kernel<float>), ST2_KFN(feature_sums_vec_kernel<__half>)});

@@ -162,6 +162,17 @@ __global__ void gram_finalize_partials_kernel(const float* __restrict__ partials
   block_accumulate<1>(v, dst);
 }
 
+// strip's un-normalised Gram sum: sum over the splits (in double), stored fp32
+__global__ void gram_reduce_partials_kernel(const float* __restrict__ partials, int nsplit,
+                                            float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += (double)partials[(long long)k * n + i];
+    out[i] = (float)s;
+  }
+}
+
 }  // namespace
 
 struct TcGramPlan {
@@ -217,13 +228,27 @@ static int launch_gn(st2_ctx* ctx, TcGramPlan* p) {
   return 0;
 }
 
-int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double* sum_dsq) {
-  int rc;
+static int launch_mma(st2_ctx* ctx, TcGramPlan* p) {
   switch (p->gn) {
-    case 256: rc = launch_gn<256>(ctx, p); break;
-    case 128: rc = launch_gn<128>(ctx, p); break;
-    default:  rc = launch_gn<64>(ctx, p); break;
+    case 256: return launch_gn<256>(ctx, p);
+    case 128: return launch_gn<128>(ctx, p);
+    default:  return launch_gn<64>(ctx, p);
   }
+}
+
+int tc_gram_sum_launch(st2_ctx* ctx, TcGramPlan* p, float* Gsum) {
+  int rc = launch_mma(ctx, p);
+  if (rc) return rc;
+  const long long n = (long long)p->g.C * p->g.C;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+  gram_reduce_partials_kernel<<<blocks, 256, 0, ctx->stream>>>(p->partials, p->g.splits, Gsum, n);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double* sum_dsq) {
+  int rc = launch_mma(ctx, p);
   if (rc) return rc;
   const long long n = (long long)p->g.C * p->g.C;
   int blocks = (int)((n + 255) / 256);
@@ -233,3 +258,6 @@ int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
+
+static St2KernelReg g_reg_gram_tc({ST2_KFN(tc_gram_kernel<256>), ST2_KFN(tc_gram_kernel<128>), ST2_KFN(tc_gram_kernel<64>),
+                                      ST2_KFN(gram_reduce_partials_kernel), ST2_KFN(gram_finalize_partials_kernel)});

@@ -9,14 +9,16 @@ enum { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_RAW = 2 };
 // first layer: x fp32 NCHW (3 planes) -> NHWC T (64 ch), bias + ReLU     (K1, conv1_1)
 template <typename T>
 int launch_conv_first_fwd(st2_ctx* ctx, const float* x, const float* w_fwd /*[27][64]*/, const float* bias,
-                          T* out, int H, int W);
+                          T* out, int H, int W, long long x_plane_stride = 0, int lo = 0, int hi = 0);
 // first layer data gradient: g NHWC T (64 ch) -> fp32 NCHW (3 planes)    (K2, conv1_1)
 template <typename T>
 int launch_conv_first_bwd(st2_ctx* ctx, const T* g, const float* w_bwd /*[9][64][3] flipped*/, float* gx,
-                          int H, int W);
+                          int H, int W, int lo = 0, int hi = 0);
 // exact fp32 3x3 conv on NHWC float; w = [tap][cin][cout]; epi per EPI_*; act used by EPI_MASK
 int launch_conv_exact(st2_ctx* ctx, const float* in, const float* w, const float* bias, const float* act,
-                      float* out, int H, int W, int cin, int cout, int epi);
+                      float* out, int H, int W, int cin, int cout, int epi, int lo = 0, int hi = 0);
+// Row strips: `lo` / `hi` = 1 when the row above the first / below the last of the H rows passed is an
+// addressable halo row holding the neighbouring strip's data (0: outside is the zero pad).
 template <typename T>
 int launch_pool_fwd(st2_ctx* ctx, const T* in, T* out, int C, int H, int W);
 // route g_pool back to the window's first maximum of `act`; apply_mask multiplies by act > 0
@@ -46,6 +48,10 @@ int launch_gram_generic(st2_ctx* ctx, const T* F, int C, long long HW, long long
 // D = Gd/(C*HW) - A (A nullable -> D = G); out_f32 = D ; *sum_dsq += sum D^2
 int launch_gram_finalize(st2_ctx* ctx, const double* Gd, const float* A, float* D, int C, long long HW,
                          double* sum_dsq);
+// row strips: Gd -> fp32 un-normalised sum (all-reduced by the caller), then D = Gs/(C*HW_total) - A
+int launch_gram_acc_to_f32(st2_ctx* ctx, const double* Gd, float* out, int C);
+int launch_gram_from_sum(st2_ctx* ctx, const float* Gs, const float* A, float* D, int C, double HW_total,
+                         double* sum_dsq);
 // raw[p,i] = sum_j D[i,j] F[p,j]  (strided, any T); *sum_rawsq += sum raw^2
 template <typename T>
 int launch_style_grad_generic(st2_ctx* ctx, const T* F, const float* D, T* raw, int C, long long HW,
@@ -57,10 +63,18 @@ int launch_import_nchw(st2_ctx* ctx, const float* nchw, T* nhwc, int C, int H, i
 int launch_add_inplace(st2_ctx* ctx, float* y, const float* x, float coef_host, const double* coef_dev,
                        long long n);
 
+// ---- st2_pixel.cu: st2_pixel_terms on a row strip (x planes xps floats apart; wrap = 0: rows -1 and H
+// of x are addressable halo rows) ------------------------------------------------------------------
+int pixel_terms_strip(st2_ctx* ctx, const float* x, long long xps, int wrap, const float* bwd, float* grad_out,
+                      int C, int H, int W, float tv, float tv_power, float p, float p_power, float divisor,
+                      double* scal);
+
 // ---- st2_conv_tc.cu (tcgen05 implicit GEMM, fp16 NHWC) -----------------------------------------
 struct TcConvPlan;     // tensor maps + tile geometry for one (layer, direction, canvas)
+// halo = 1 (row strips): `in` points at a buffer of H + 2 rows whose first and last row are halo rows
+// (neighbouring strip's data, or zeros at the canvas edge); outputs are the H interior rows.
 int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, int H, int W, int cin,
-                        int cout, int taps, TcConvPlan** out);
+                        int cout, int taps, TcConvPlan** out, int halo = 0);
 void tc_conv_plan_destroy(TcConvPlan* p);
 // epi per EPI_*; bias fp32 (EPI_BIAS_RELU); act fp16 NHWC (EPI_MASK); sumsq nullable (sum of fp32 outputs^2)
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
@@ -71,6 +85,8 @@ int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGr
 void tc_gram_plan_destroy(TcGramPlan* p);
 // D = F^T F / (C*HW) - A (A nullable); *sum_dsq += sum D^2 (nullable)
 int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double* sum_dsq);
+// row strips: Gsum (C x C fp32) = F^T F of this strip, un-normalised
+int tc_gram_sum_launch(st2_ctx* ctx, TcGramPlan* p, float* Gsum);
 
 // ---- st2_elementwise.cu: 16-byte-vectorised variants (fall back to the scalar kernels) ---------
 template <typename T> int launch_pool_fwd_v(st2_ctx* ctx, const T* in, T* out, int C, int H, int W);

@@ -23,7 +23,10 @@ inline int ew_grid(long long work_items, int sm_count) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                      const float* __restrict__ bias, T* __restrict__ out, int H, int W) {
+                      const float* __restrict__ bias, T* __restrict__ out, int H, int W, long long xps,
+                      int lo, int hi) {
+  // x: row 0 of plane 0 of the H local rows; planes xps floats apart; rows -lo .. H-1+hi addressable
+  // (halo rows of a row strip), anything outside is the zero pad.
   __shared__ __align__(16) float sw[27 * 64];          // [tap][ci][co]
   __shared__ __align__(16) float sb[64];
   __shared__ float sx[3][3][258];
@@ -41,7 +44,7 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
       const int c = i / (3 * 258), r = (i / 258) % 3, col = i % 258;
       const int hh = h + r - 1, ww = w0 + col - 1;
       float v = 0.f;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[((long long)c * H + hh) * W + ww]);
+      if (hh >= -lo && hh < H + hi && ww >= 0 && ww < W) v = __ldg(&x[(long long)c * xps + (long long)hh * W + ww]);
       sx[c][r][col] = v;
     }
     __syncthreads();
@@ -148,7 +151,7 @@ template <> struct Load8<float> {
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_first_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int H,
-                      int W) {
+                      int W, int lo, int hi) {
   __shared__ __align__(16) float sw[9][8][28];          // [tap][channel group][8 co x 3 ci (+4 pad)]
   for (int i = threadIdx.x; i < 9 * 64 * 3; i += blockDim.x) {
     const int ci = i % 3, co = (i / 3) % 64, tap = i / 192;
@@ -171,7 +174,7 @@ conv_first_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, floa
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int hh = h + r - 1;
-        if (hh < 0 || hh >= H) continue;               // warp-uniform
+        if (hh < -lo || hh >= H + hi) continue;        // warp-uniform
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           typename Load8<T>::raw_t raw[4];
@@ -238,7 +241,8 @@ conv_first_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, floa
 template <int EPI>
 __global__ void __launch_bounds__(256)
 conv_exact_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                  const float* __restrict__ act, float* __restrict__ out, int H, int W, int cin, int cout) {
+                  const float* __restrict__ act, float* __restrict__ out, int H, int W, int cin, int cout,
+                  int lo, int hi) {
   __shared__ __align__(16) float As[16][64 + 4];
   __shared__ __align__(16) float Bs[16][64];
   const int tiles_w = (W + 7) / 8;
@@ -255,7 +259,7 @@ conv_exact_kernel(const float* __restrict__ in, const float* __restrict__ w, con
   float acc[4][4] = {};
   for (int tap = 0; tap < 9; ++tap) {
     const int hh = lph + tap / 3 - 1, wc = lpw + tap % 3 - 1;
-    const bool inb = hh >= 0 && hh < H && wc >= 0 && wc < W;
+    const bool inb = hh >= -lo && hh < H + hi && wc >= 0 && wc < W;
     const float* ip = in + ((long long)hh * W + wc) * cin;
     const float* wp = w + (long long)tap * cin * cout;
     for (int c0 = 0; c0 < cin; c0 += 16) {
@@ -456,6 +460,31 @@ __global__ void gram_finalize_kernel(const double* __restrict__ Gd, const float*
   block_accumulate<1>(v, dst);
 }
 
+// Row strips: the strip's un-normalised Gram sum as fp32 (what gets all-reduced), and the finalize from
+// the all-reduced sum with the whole canvas' pixel count.
+__global__ void gram_acc_to_f32_kernel(const double* __restrict__ Gd, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)Gd[i];
+}
+
+__global__ void gram_from_sum_kernel(const float* __restrict__ Gs, const float* __restrict__ A,
+                                     float* __restrict__ D, int C, double HW, double* sum_dsq) {
+  const long long n = (long long)C * C;
+  const float denom = (float)((double)C * HW);
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float g = Gs[i] / denom;
+    if (A != nullptr) g -= A[i];
+    D[i] = g;
+    acc = fmaf(g, g, acc);
+  }
+  float v[1] = {acc};
+  double* dst[1] = {sum_dsq};
+  block_accumulate<1>(v, dst);
+}
+
 // raw[p, i] = sum_j D[i, j] F[p, j]; block = 64 pixels x 64 channels i, K step 16 channels j
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -559,38 +588,38 @@ __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restric
 // =============================================================================== launch wrappers
 template <typename T>
 int launch_conv_first_fwd(st2_ctx* ctx, const float* x, const float* w, const float* bias, T* out, int H,
-                          int W) {
+                          int W, long long xps, int lo, int hi) {
   const int items = H * ((W + 255) / 256);
   const int blocks = items < ctx->sm_count * 2 ? items : ctx->sm_count * 2;
-  conv_first_fwd_kernel<T><<<blocks, 256, 0, ctx->stream>>>(x, w, bias, out, H, W);
+  conv_first_fwd_kernel<T><<<blocks, 256, 0, ctx->stream>>>(x, w, bias, out, H, W, xps ? xps : (long long)H * W, lo, hi);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
-template int launch_conv_first_fwd<float>(st2_ctx*, const float*, const float*, const float*, float*, int, int);
-template int launch_conv_first_fwd<__half>(st2_ctx*, const float*, const float*, const float*, __half*, int, int);
+template int launch_conv_first_fwd<float>(st2_ctx*, const float*, const float*, const float*, float*, int, int, long long, int, int);
+template int launch_conv_first_fwd<__half>(st2_ctx*, const float*, const float*, const float*, __half*, int, int, long long, int, int);
 
 template <typename T>
-int launch_conv_first_bwd(st2_ctx* ctx, const T* g, const float* w, float* gx, int H, int W) {
+int launch_conv_first_bwd(st2_ctx* ctx, const T* g, const float* w, float* gx, int H, int W, int lo, int hi) {
   const long long hw = (long long)H * W;
   long long blocks = (long long)((W + 15) / 16) * ((H + 7) / 8);
   if (blocks > (long long)ctx->sm_count * 8) blocks = (long long)ctx->sm_count * 8;
-  conv_first_bwd_kernel<T><<<(int)blocks, 256, 0, ctx->stream>>>(g, w, gx, H, W);
+  conv_first_bwd_kernel<T><<<(int)blocks, 256, 0, ctx->stream>>>(g, w, gx, H, W, lo, hi);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
-template int launch_conv_first_bwd<float>(st2_ctx*, const float*, const float*, float*, int, int);
-template int launch_conv_first_bwd<__half>(st2_ctx*, const __half*, const float*, float*, int, int);
+template int launch_conv_first_bwd<float>(st2_ctx*, const float*, const float*, float*, int, int, int, int);
+template int launch_conv_first_bwd<__half>(st2_ctx*, const __half*, const float*, float*, int, int, int, int);
 
 int launch_conv_exact(st2_ctx* ctx, const float* in, const float* w, const float* bias, const float* act,
-                      float* out, int H, int W, int cin, int cout, int epi) {
+                      float* out, int H, int W, int cin, int cout, int epi, int lo, int hi) {
   if (cin % 16 || cout % 64) return st2_fail(ctx, ST2_ERR_ARG, "conv_exact: cin %% 16 / cout %% 64");
   dim3 grid(((H + 7) / 8) * ((W + 7) / 8), cout / 64);
   if (epi == EPI_BIAS_RELU)
-    conv_exact_kernel<EPI_BIAS_RELU><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout);
+    conv_exact_kernel<EPI_BIAS_RELU><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout, lo, hi);
   else if (epi == EPI_MASK)
-    conv_exact_kernel<EPI_MASK><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout);
+    conv_exact_kernel<EPI_MASK><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout, lo, hi);
   else
-    conv_exact_kernel<EPI_RAW><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout);
+    conv_exact_kernel<EPI_RAW><<<grid, 256, 0, ctx->stream>>>(in, w, bias, act, out, H, W, cin, cout, lo, hi);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -664,6 +693,20 @@ int launch_gram_finalize(st2_ctx* ctx, const double* Gd, const float* A, float* 
   return 0;
 }
 
+int launch_gram_acc_to_f32(st2_ctx* ctx, const double* Gd, float* out, int C) {
+  gram_acc_to_f32_kernel<<<ew_grid((long long)C * C, ctx->sm_count), kThreads, 0, ctx->stream>>>(Gd, out, (long long)C * C);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int launch_gram_from_sum(st2_ctx* ctx, const float* Gs, const float* A, float* D, int C, double HW_total,
+                         double* sum_dsq) {
+  gram_from_sum_kernel<<<ew_grid((long long)C * C, ctx->sm_count), kThreads, 0, ctx->stream>>>(Gs, A, D, C, HW_total,
+                                                                                               sum_dsq);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 template <typename T>
 int launch_style_grad_generic(st2_ctx* ctx, const T* F, const float* D, T* raw, int C, long long HW,
                               long long sp, long long sc, double* sum_rawsq) {
@@ -705,3 +748,14 @@ int launch_add_inplace(st2_ctx* ctx, float* y, const float* x, float coef_host, 
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
+
+static St2KernelReg g_reg_layers({
+    ST2_KFN(conv_first_fwd_kernel<float>), ST2_KFN(conv_first_fwd_kernel<__half>), ST2_KFN(conv_first_bwd_kernel<float>),
+    ST2_KFN(conv_first_bwd_kernel<__half>), ST2_KFN(conv_exact_kernel<EPI_BIAS_RELU>), ST2_KFN(conv_exact_kernel<EPI_MASK>),
+    ST2_KFN(conv_exact_kernel<EPI_RAW>), ST2_KFN(pool_fwd_kernel<float>), ST2_KFN(pool_fwd_kernel<__half>),
+    ST2_KFN(pool_bwd_kernel<float>), ST2_KFN(pool_bwd_kernel<__half>), ST2_KFN(combine_kernel<float>),
+    ST2_KFN(combine_kernel<__half>), ST2_KFN(feature_sums_kernel<float>), ST2_KFN(feature_sums_kernel<__half>),
+    ST2_KFN(gram_generic_kernel<float>), ST2_KFN(gram_generic_kernel<__half>), ST2_KFN(gram_finalize_kernel),
+    ST2_KFN(gram_acc_to_f32_kernel), ST2_KFN(gram_from_sum_kernel), ST2_KFN(style_grad_generic_kernel<float>),
+    ST2_KFN(style_grad_generic_kernel<__half>), ST2_KFN(export_nchw_kernel<float>), ST2_KFN(export_nchw_kernel<__half>),
+    ST2_KFN(import_nchw_kernel<float>), ST2_KFN(import_nchw_kernel<__half>), ST2_KFN(add_inplace_kernel)});

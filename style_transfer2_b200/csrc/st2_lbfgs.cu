@@ -510,3 +510,9 @@ int st2_lbfgs_export(st2_lbfgs* o, int* count_out, float* s_dev, float* y_dev, d
 }
 
 }  // extern "C"
+
+static St2KernelReg g_reg_lbfgs({
+    ST2_KFN(lbfgs_pass_a<1>), ST2_KFN(lbfgs_pass_a<4>), ST2_KFN(lbfgs_pass_b<1>), ST2_KFN(lbfgs_pass_b<4>),
+    ST2_KFN(lbfgs_pass_g<1>), ST2_KFN(lbfgs_pass_g<4>), ST2_KFN(lbfgs_pass_y<1>), ST2_KFN(lbfgs_pass_y<4>),
+    ST2_KFN(lbfgs_take_g), ST2_KFN(lbfgs_coefficients), ST2_KFN(lbfgs_clear_sums), ST2_KFN(lbfgs_accept),
+    ST2_KFN(lbfgs_store_y_dots)});

@@ -22,6 +22,11 @@ const BlobInfo g_blobs[ST2_NUM_BLOBS] = {
 
 static std::string g_create_error;
 
+std::vector<const void*>& st2_kernel_registry() {
+  static std::vector<const void*> v;
+  return v;
+}
+
 int st2_fail(st2_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -146,9 +151,10 @@ __global__ void coef_kernel(EvalSpec es, double* scal) {
 }
 
 // worker.py:279-301: totals in the reference's accumulation order
-__global__ void final_kernel(EvalSpec es, double* scal) {
+__global__ void final_kernel(EvalSpec es, double* scal, const int* halo_err) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double* g = scal + ST2_SCAL_GLOBAL_BASE;
+  g[ST2_G_HALO_TIMEOUT] = (halo_err != nullptr && *halo_err != 0) ? 1.0 : 0.0;
   double scd = 0.0;
   for (int k = 0; k < es.n; ++k) {
     const int b = es.order[k];
@@ -168,9 +174,12 @@ __global__ void final_kernel(EvalSpec es, double* scal) {
 }
 
 struct Blob {
-  int C = 0, H = 0, W = 0;
-  void* act = nullptr;        // T NHWC (data: caller's fp32 NCHW x)
-  void* grad = nullptr;       // T NHWC gradient w.r.t. the (post-ReLU) blob
+  int C = 0, H = 0, W = 0;    // H: rows held here (the strip's rows when the canvas is row-tiled)
+  int Hg = 0;                 // rows of the whole canvas at this level
+  void* act = nullptr;        // T NHWC (data: caller's fp32 NCHW x); strips: first interior row
+  void* grad = nullptr;       // T NHWC gradient w.r.t. the (post-ReLU) blob; strips: first interior row
+  void* act_pad = nullptr;    // strips: start of the top halo row (act - one row)
+  void* grad_pad = nullptr;
   void* fc = nullptr;         // content target, same layout as act
   void* sraw = nullptr;       // unscaled style gradient D F
   void* inj = nullptr;        // imported diff for the model-seam backward
@@ -183,6 +192,7 @@ struct Blob {
   TcConvPlan* tc_style = nullptr;
   TcGramPlan* tc_gram = nullptr;
   long long n() const { return (long long)C * H * W; }
+  double n_total() const { return (double)C * (double)Hg * (double)W; }
 };
 
 struct Inject {
@@ -195,10 +205,153 @@ struct Inject {
 
 }  // namespace
 
+// ---- row strips: one canvas split over several GPUs ------------------------------
+// Every activation / gradient tensor of a strip carries one halo row above and below its own rows.
+// After a layer is produced, a push kernel stores the strip's first / last row straight into the
+// neighbouring strips' halo rows (peer memory: CUDA IPC mapping over NVLink, or the same address
+// space when several strips share a GPU) and raises a flag there; the consumer's next convolution is
+// preceded by a one-thread kernel that spins on its own flags.  No host synchronisation, no NCCL on
+// the halo path.  All of a strip's halo-carrying buffers live in ONE allocation (the slab) so a
+// neighbour needs a single IPC handle; its layout is a pure function of (rows, W, element size).
+constexpr int kSlots = 2 * ST2_NUM_BLOBS;      // slot b: act of blob b (0 = x); ST2_NUM_BLOBS + b: grad of blob b
+constexpr size_t kSlabHeader = 4096;
+struct SlabHeader {
+  unsigned long long flag_from[2][kSlots];     // [0]: raised by the strip above, [1]: by the strip below
+  unsigned int counters[2];
+  int err;                                     // sticky: a wait timed out
+};
+static_assert(sizeof(SlabHeader) <= kSlabHeader, "slab header");
+
+struct StripLayout {
+  int rows[ST2_NUM_BLOBS], W[ST2_NUM_BLOBS];
+  size_t act_off[ST2_NUM_BLOBS], grad_off[ST2_NUM_BLOBS], row_bytes[ST2_NUM_BLOBS];
+  size_t xp_off, total;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static StripLayout strip_layout(int rows0, int W0, size_t esz) {
+  StripLayout L;
+  size_t off = kSlabHeader;
+  L.xp_off = off;
+  off = align_up(off + sizeof(float) * 3 * (size_t)(rows0 + 2) * W0, 1024);
+  int h = rows0, w = W0;
+  for (int i = 0; i < ST2_NUM_BLOBS; ++i) {
+    if (g_blobs[i].kind == KIND_POOL) { h = pool_extent(h); w = pool_extent(w); }
+    L.rows[i] = h; L.W[i] = w;
+    L.row_bytes[i] = (size_t)w * g_blobs[i].channels * esz;
+    L.act_off[i] = L.grad_off[i] = 0;
+    if (i == 0) continue;
+    L.act_off[i] = off;
+    off = align_up(off + L.row_bytes[i] * (size_t)(h + 2), 1024);
+    L.grad_off[i] = off;
+    off = align_up(off + L.row_bytes[i] * (size_t)(h + 2), 1024);
+  }
+  L.total = off;
+  return L;
+}
+
+struct HaloPush {
+  const unsigned char* src[2];          // my first / last interior row
+  unsigned char* dst[2];                // the bottom halo row of the strip above / top halo row of the strip below
+  unsigned long long* flag[2];          // the flag to raise over there
+  long long src_seg_stride, dst_seg_stride[2];
+  long long seg_bytes;
+  int nseg;
+  unsigned long long epoch;
+  unsigned int* counters;
+};
+
+// grid (blocks, 2): y = 0 pushes up, y = 1 pushes down.  The last block of a direction to finish raises the flag.
+__global__ void halo_push_kernel(const HaloPush a) {
+  const int dir = blockIdx.y;
+  if (a.dst[dir] == nullptr) return;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (int sgm = 0; sgm < a.nseg; ++sgm) {
+    const unsigned char* sp = a.src[dir] + sgm * a.src_seg_stride;
+    unsigned char* dp = a.dst[dir] + sgm * a.dst_seg_stride[dir];
+    if ((a.seg_bytes & 15) == 0 && (((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(sp);
+      uint4* d4 = reinterpret_cast<uint4*>(dp);
+      for (long long i = tid; i < (a.seg_bytes >> 4); i += nth) d4[i] = s4[i];
+    } else {
+      const unsigned int* s1 = reinterpret_cast<const unsigned int*>(sp);
+      unsigned int* d1 = reinterpret_cast<unsigned int*>(dp);
+      for (long long i = tid; i < (a.seg_bytes >> 2); i += nth) d1[i] = s1[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&a.counters[dir], 1u);
+    if (prev == gridDim.x - 1) {
+      a.counters[dir] = 0;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[dir]), "l"(a.epoch) : "memory");
+    }
+  }
+}
+
+// thread 0 waits for the strip above, thread 1 for the strip below (null = nobody there)
+__global__ void halo_wait_kernel(const unsigned long long* f_up, const unsigned long long* f_dn,
+                                 unsigned long long epoch, int* err) {
+  const unsigned long long* f = threadIdx.x == 0 ? f_up : f_dn;
+  if (f == nullptr || *reinterpret_cast<volatile int*>(err) != 0) return;
+  unsigned long long t0, t1, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= epoch) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) { atomicExch(err, 1); break; }     // 10 s: the neighbour died; fail loudly, don't hang
+    __nanosleep(64);
+  }
+}
+
+// x (3 dense planes of rows x W) -> interior rows of the padded planes
+__global__ void pack_x_kernel(const float* __restrict__ x, float* __restrict__ xp, int rows, int W) {
+  const long long plane = (long long)rows * W, total = 3 * plane;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / plane);
+    const long long r = i - (long long)c * plane;
+    xp[(long long)c * (rows + 2) * W + W + r] = x[i];
+  }
+}
+
+// the all-reduced partial sums -> their scalar-block slots
+__global__ void scatter_sums_kernel(const double* __restrict__ red, double* __restrict__ scal) {
+  const int b = threadIdx.x;
+  if (b >= ST2_NUM_BLOBS) return;
+  double* sb = scal + b * ST2_SCAL_PER_BLOB;
+  sb[SB_C_SUMSQ] = red[3 * b + 0];
+  sb[SB_D_SUMSQ] = red[3 * b + 1];
+  sb[SB_S_RAWSQ] = red[3 * b + 2];
+}
+
 struct st2_plan {
   st2_ctx* ctx;
-  int H, W, prec;
+  int H, W, prec;             // H: rows held here
   size_t esz;
+  // row-strip state (strip == false: the plan holds the whole canvas)
+  bool strip = false, edge_top = true, edge_bot = true;
+  int rank = 0, world = 1, row0 = 0, H_total = 0;
+  unsigned char* slab = nullptr;
+  StripLayout lay;
+  unsigned char* peer[2] = {nullptr, nullptr};      // slab of the strip above / below (circular)
+  bool peer_ipc[2] = {false, false};
+  StripLayout peer_lay[2];
+  unsigned long long epoch[kSlots] = {};
+  float* xp = nullptr;                               // padded copy of x: 3 x (H + 2) x W
+  float* gram_red = nullptr;                         // strip Gram sums, fp32, all-reduced by the caller
+  long long gram_red_off[ST2_NUM_BLOBS] = {};
+  long long gram_red_used = 0;
+  double* red = nullptr;                             // 3 partial sums per blob, all-reduced by the caller
+  // evaluation state carried between the phases
+  EvalSpec es;
+  Inject inj[ST2_NUM_BLOBS];
+  int eval_top = 0, eval_want_grad = 0, eval_phase = 0;
+  const float* eval_x = nullptr;
   Blob b[ST2_NUM_BLOBS];
   double* scal = nullptr;
   double* gram_acc = nullptr;     // 512 x 512 doubles
@@ -213,10 +366,74 @@ struct st2_plan {
 
 static inline bool host_w_on(float w) { return fabsf(w) > 1e-15f; }
 
+// Push this strip's first / last row of `slot` into the neighbours' halo rows, then wait for theirs.
+// slot < ST2_NUM_BLOBS: activation of blob `slot` (0 = the padded x, circular for the TV term);
+// otherwise the gradient of blob slot - ST2_NUM_BLOBS.
+static int halo_exchange(st2_plan* pl, int slot) {
+  st2_ctx* ctx = pl->ctx;
+  if (!pl->peer[0] || !pl->peer[1]) return st2_fail(ctx, ST2_ERR_STATE, "strip plan: neighbours not attached");
+  const bool is_x = (slot == 0);
+  const int b = slot % ST2_NUM_BLOBS;
+  const bool is_grad = slot >= ST2_NUM_BLOBS;
+  const bool up = is_x || !pl->edge_top, dn = is_x || !pl->edge_bot;
+  if (!up && !dn) return 0;
+  const unsigned long long epoch = ++pl->epoch[slot];
+  SlabHeader* mine = reinterpret_cast<SlabHeader*>(pl->slab);
+  HaloPush a;
+  memset(&a, 0, sizeof(a));
+  a.epoch = epoch;
+  a.counters = mine->counters;
+  const StripLayout& L = pl->lay;
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? up : dn)) continue;
+    const StripLayout& PL = pl->peer_lay[side];
+    SlabHeader* theirs = reinterpret_cast<SlabHeader*>(pl->peer[side]);
+    a.flag[side] = &theirs->flag_from[side == 0 ? 1 : 0][slot];     // I am its neighbour below (0) / above (1)
+    if (is_x) {
+      // planar: 3 segments of one row; their padded plane may have a different row count
+      const long long W = pl->W;
+      a.nseg = 3; a.seg_bytes = W * 4;
+      a.src_seg_stride = (long long)(pl->H + 2) * W * 4;
+      a.dst_seg_stride[side] = (long long)(PL.rows[0] + 2) * W * 4;
+      const unsigned char* base = pl->slab + L.xp_off;
+      a.src[side] = base + (side == 0 ? 1 : pl->H) * W * 4;         // first / last interior row of plane 0
+      unsigned char* pbase = pl->peer[side] + PL.xp_off;
+      a.dst[side] = pbase + (side == 0 ? (long long)(PL.rows[0] + 1) * W * 4 : 0);
+    } else {
+      const size_t rb = L.row_bytes[b];
+      a.nseg = 1; a.seg_bytes = (long long)rb;
+      const unsigned char* base = pl->slab + (is_grad ? L.grad_off[b] : L.act_off[b]);
+      a.src[side] = base + (side == 0 ? (size_t)1 : (size_t)L.rows[b]) * rb;
+      unsigned char* pbase = pl->peer[side] + (is_grad ? PL.grad_off[b] : PL.act_off[b]);
+      a.dst[side] = pbase + (side == 0 ? (size_t)(PL.rows[b] + 1) * rb : 0);
+    }
+  }
+  long long vecs = a.seg_bytes / 16 * a.nseg;
+  int blocks = (int)((vecs + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 32) blocks = 32;
+  halo_push_kernel<<<dim3(blocks, 2), 256, 0, ctx->stream>>>(a);
+  ST2_LAUNCH_CHECK(ctx);
+  halo_wait_kernel<<<1, 2, 0, ctx->stream>>>(up ? &mine->flag_from[0][slot] : nullptr,
+                                             dn ? &mine->flag_from[1][slot] : nullptr, epoch, &mine->err);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 template <typename T>
 static int forward_impl(st2_plan* pl, const float* x, int top) {
   st2_ctx* ctx = pl->ctx;
   pl->b[0].act = const_cast<float*>(x);
+  const int lo = (pl->strip && !pl->edge_top) ? 1 : 0, hi = (pl->strip && !pl->edge_bot) ? 1 : 0;
+  if (pl->strip) {
+    // padded copy of x with the neighbours' boundary rows (circular: the TV term wraps around the canvas)
+    long long blocks = ((long long)3 * pl->H * pl->W + 255) / 256;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    pack_x_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(x, pl->xp, pl->H, pl->W);
+    ST2_LAUNCH_CHECK(ctx);
+    int rc = halo_exchange(pl, 0);
+    if (rc) return rc;
+  }
   for (int i = 1; i <= top; ++i) {
     Blob& cur = pl->b[i];
     Blob& below = pl->b[i - 1];
@@ -227,10 +444,14 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
       const int ci = g_blobs[i].conv_index;
       if (!ctx->w_oihw[ci]) return st2_fail(ctx, ST2_ERR_STATE, "weights of %s not loaded", g_blobs[i].name);
       if (ci == 0) {
-        rc = launch_conv_first_fwd<T>(ctx, x, ctx->wf32_fwd[0], ctx->bias[0], (T*)cur.act, cur.H, cur.W);
+        if (pl->strip)
+          rc = launch_conv_first_fwd<T>(ctx, pl->xp + pl->W, ctx->wf32_fwd[0], ctx->bias[0], (T*)cur.act, cur.H, cur.W,
+                                        (long long)(pl->H + 2) * pl->W, lo, hi);
+        else
+          rc = launch_conv_first_fwd<T>(ctx, x, ctx->wf32_fwd[0], ctx->bias[0], (T*)cur.act, cur.H, cur.W);
       } else if (pl->prec == ST2_PREC_FP32) {
         rc = launch_conv_exact(ctx, (const float*)below.act, ctx->wf32_fwd[ci], ctx->bias[ci], nullptr,
-                               (float*)cur.act, cur.H, cur.W, below.C, cur.C, EPI_BIAS_RELU);
+                               (float*)cur.act, cur.H, cur.W, below.C, cur.C, EPI_BIAS_RELU, lo, hi);
       } else {
         rc = tc_conv_launch(ctx, cur.tc_fwd, ctx->bias[ci], nullptr, (__half*)cur.act, EPI_BIAS_RELU, 1.f, nullptr);
       }
@@ -238,6 +459,8 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
       rc = launch_pool_fwd_v<T>(ctx, (const T*)below.act, (T*)cur.act, below.C, below.H, below.W);
     }
     if (rc) return rc;
+    // the next convolution reads one row of the neighbouring strips
+    if (pl->strip && i < top && g_blobs[i + 1].kind == KIND_CONV && (rc = halo_exchange(pl, i))) return rc;
   }
   pl->x_cur = x;
   pl->top_cur = top;
@@ -250,6 +473,7 @@ template <typename T>
 static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_out) {
   st2_ctx* ctx = pl->ctx;
   if (top > pl->top_cur) return st2_fail(ctx, ST2_ERR_STATE, "backward above the last forward's top blob");
+  const int lo = (pl->strip && !pl->edge_top) ? 1 : 0, hi = (pl->strip && !pl->edge_bot) ? 1 : 0;
   if (top == 0) {
     ST2_CUDA(ctx, cudaMemsetAsync(grad_out, 0, sizeof(float) * pl->b[0].n(), ctx->stream));
   }
@@ -275,14 +499,16 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
     const bool below_conv = g_blobs[i - 1].kind == KIND_CONV;
     const int mask_below = (below_conv && !inj[i - 1].on) ? 1 : 0;
     const int bcat = !is_conv ? 2 : (g_blobs[i].conv_index == 0 ? 1 : (pl->prec == ST2_PREC_FP32 ? 8 : 0));
+    // the data-gradient convolution reads one row of the neighbouring strips' gradient
+    if (pl->strip && is_conv && (rc = halo_exchange(pl, ST2_NUM_BLOBS + i))) return rc;
     ProfScope ps(ctx, bcat);
     if (is_conv) {
       const int ci = g_blobs[i].conv_index;
       if (ci == 0) {
-        rc = launch_conv_first_bwd<T>(ctx, (const T*)cur.grad, ctx->wf32_bwd[0], grad_out, cur.H, cur.W);
+        rc = launch_conv_first_bwd<T>(ctx, (const T*)cur.grad, ctx->wf32_bwd[0], grad_out, cur.H, cur.W, lo, hi);
       } else if (pl->prec == ST2_PREC_FP32) {
         rc = launch_conv_exact(ctx, (const float*)cur.grad, ctx->wf32_bwd[ci], nullptr, (const float*)below.act,
-                               (float*)below.grad, cur.H, cur.W, cur.C, below.C, mask_below ? EPI_MASK : EPI_RAW);
+                               (float*)below.grad, cur.H, cur.W, cur.C, below.C, mask_below ? EPI_MASK : EPI_RAW, lo, hi);
       } else {
         rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad,
                             mask_below ? EPI_MASK : EPI_RAW, 1.f, nullptr);
@@ -325,16 +551,44 @@ static int gram_of_blob(st2_plan* pl, int blob, const float* A, float* D, double
   return launch_gram_finalize(ctx, pl->gram_acc, A, D, B.C, HW, sum_dsq);
 }
 
+// row strips: un-normalised Gram sum of this strip's rows of `blob` -> out (C x C fp32)
+template <typename T>
+static int gram_sum_of_blob(st2_plan* pl, int blob, float* out) {
+  st2_ctx* ctx = pl->ctx;
+  Blob& B = pl->b[blob];
+  const long long HW = (long long)B.H * B.W;
+  if (blob != 0 && pl->prec == ST2_PREC_FP16 && g_blobs[blob].kind == KIND_CONV && B.C % 64 == 0 &&
+      !getenv("ST2_NO_TC_GRAM")) {
+    if (!B.tc_gram) {
+      int rc0 = tc_gram_plan_create(ctx, (const __half*)B.act, B.C, HW, &B.tc_gram);
+      if (rc0) return rc0;
+    }
+    return tc_gram_sum_launch(ctx, B.tc_gram, out);
+  }
+  ST2_CUDA(ctx, cudaMemsetAsync(pl->gram_acc, 0, sizeof(double) * B.C * B.C, ctx->stream));
+  int rc;
+  if (blob == 0) rc = launch_gram_generic<float>(ctx, (const float*)B.act, B.C, HW, 1, HW, pl->gram_acc);
+  else rc = launch_gram_generic<T>(ctx, (const T*)B.act, B.C, HW, B.C, 1, pl->gram_acc);
+  if (rc) return rc;
+  return launch_gram_acc_to_f32(ctx, pl->gram_acc, out, B.C);
+}
+
 static int ensure(st2_ctx* ctx, void** p, size_t bytes) {
   if (*p) return 0;
   ST2_CUDA(ctx, cudaMalloc(p, bytes));
   return 0;
 }
 
+// The objective (worker.py:231-301) in four phases.  On a whole-canvas plan st2_eval runs them back to
+// back.  On a row strip the caller all-reduces (sum) one small block between consecutive phases:
+//   begin: forward; local feature sums; the strip's Gram sums            -> all-reduce gram_red (fp32)
+//   mid:   D = G - A from the global Gram; style gradient D F of the strip -> all-reduce red (3 sums / blob)
+//   end:   normalisers + coefficients; backward; pixel terms              -> all-reduce 6 pixel-space sums
+//   final: totals in the reference's accumulation order
 template <typename T>
-static int eval_impl(st2_plan* pl, const float* x, float* grad_out, int want_grad) {
+static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
   st2_ctx* ctx = pl->ctx;
-  EvalSpec es;
+  EvalSpec& es = pl->es;
   memset(&es, 0, sizeof(es));
   int top = 0;
   for (int k = 0; k < pl->order_n; ++k) {
@@ -346,72 +600,116 @@ static int eval_impl(st2_plan* pl, const float* x, float* grad_out, int want_gra
   }
   for (int b = 0; b < ST2_NUM_BLOBS; ++b) {
     es.cw[b] = pl->b[b].cw; es.sw[b] = pl->b[b].sw; es.dw[b] = pl->b[b].dw;
-    es.C[b] = pl->b[b].C; es.nelem[b] = (double)pl->b[b].n();
+    es.C[b] = pl->b[b].C; es.nelem[b] = pl->b[b].n_total();
   }
   es.tv = pl->tv; es.tv_power = pl->tv_power; es.p = pl->p; es.p_power = pl->p_power;
-  es.N = (double)pl->b[0].n();
+  es.N = pl->b[0].n_total();
+  pl->eval_top = top; pl->eval_want_grad = want_grad; pl->eval_x = x;
 
   clear_volatile_kernel<<<1, 256, 0, ctx->stream>>>(pl->scal);
   ST2_LAUNCH_CHECK(ctx);
+  if (pl->strip) ST2_CUDA(ctx, cudaMemsetAsync(pl->red, 0, sizeof(double) * 3 * ST2_NUM_BLOBS, ctx->stream));
   int rc = forward_impl<T>(pl, x, top);
   if (rc) return rc;
 
-  Inject inj[ST2_NUM_BLOBS];
+  pl->gram_red_used = 0;
+  for (int b = 0; b < ST2_NUM_BLOBS; ++b) pl->inj[b] = Inject();
   for (int k = 0; k < es.n; ++k) {
     const int b = es.order[k];
     Blob& B = pl->b[b];
     double* sb = pl->scal + b * ST2_SCAL_PER_BLOB;
+    double* c_sum = pl->strip ? pl->red + 3 * b + 0 : sb + SB_C_SUMSQ;
+    double* d_sum = pl->strip ? pl->red + 3 * b + 1 : sb + SB_D_SUMSQ;
     const bool c_on = host_w_on(B.cw), s_on = host_w_on(B.sw), d_on = host_w_on(B.dw);
     if (c_on && !B.fc) return st2_fail(ctx, ST2_ERR_STATE, "content weight on %s but no content target", g_blobs[b].name);
     if (s_on && !B.gram_target) return st2_fail(ctx, ST2_ERR_STATE, "style weight on %s but no style target", g_blobs[b].name);
     if (c_on || d_on) {
       ProfScope ps(ctx, 5);
       if (b == 0) rc = launch_feature_sums_v<float>(ctx, (const float*)B.act, c_on ? (const float*)B.fc : nullptr, B.n(),
-                                                  sb + SB_C_SUMSQ, sb + SB_D_SUMSQ);
-      else rc = launch_feature_sums_v<T>(ctx, (const T*)B.act, c_on ? (const T*)B.fc : nullptr, B.n(), sb + SB_C_SUMSQ,
-                                       sb + SB_D_SUMSQ);
+                                                  c_sum, d_sum);
+      else rc = launch_feature_sums_v<T>(ctx, (const T*)B.act, c_on ? (const T*)B.fc : nullptr, B.n(), c_sum, d_sum);
       if (rc) return rc;
     }
     if (s_on) {
       const size_t e = (b == 0) ? sizeof(float) : pl->esz;
       if ((rc = ensure(ctx, (void**)&B.D, sizeof(float) * B.C * B.C))) return rc;
       if ((rc = ensure(ctx, &B.sraw, e * B.n()))) return rc;
-      {
-        ProfScope ps(ctx, 3);
+      ProfScope ps(ctx, 3);
+      if (pl->strip) {
+        pl->gram_red_off[b] = pl->gram_red_used;
+        pl->gram_red_used += (long long)B.C * B.C;
+        if ((rc = gram_sum_of_blob<T>(pl, b, pl->gram_red + pl->gram_red_off[b]))) return rc;
+      } else {
         if ((rc = gram_of_blob<T>(pl, b, B.gram_target, B.D, sb + SB_S_GRAMSQ))) return rc;
       }
-      const long long HW = (long long)B.H * B.W;
-      ProfScope ps(ctx, 4);
-      if (want_grad) {
-        if (b == 0) {
-          rc = launch_style_grad_generic<float>(ctx, (const float*)B.act, B.D, (float*)B.sraw, B.C, HW, 1, HW,
-                                                sb + SB_S_RAWSQ);
-        } else if (pl->prec == ST2_PREC_FP16 && g_blobs[b].kind == KIND_CONV && B.C % 64 == 0) {
-          if ((rc = ensure(ctx, (void**)&B.Dh, sizeof(__half) * B.C * B.C))) return rc;
-          if (!B.tc_style &&
-              (rc = tc_conv_plan_create(ctx, (const __half*)B.act, B.Dh, B.H, B.W, B.C, B.C, 1, &B.tc_style)))
-            return rc;
-          style_scale_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(B.D, B.Dh, B.C, sb);
-          ST2_LAUNCH_CHECK(ctx);
-          rc = tc_conv_launch(ctx, B.tc_style, nullptr, nullptr, (__half*)B.sraw, EPI_RAW, 1.f, sb + SB_S_RAWSQ);
-        } else {
-          rc = launch_style_grad_generic<T>(ctx, (const T*)B.act, B.D, (T*)B.sraw, B.C, HW, B.C, 1, sb + SB_S_RAWSQ);
-        }
-        if (rc) return rc;
-      } else {
-        // loss-only evaluation still freezes the style normaliser (worker.py:265-266), which needs |D F|
-        if (b == 0)
-          rc = launch_style_grad_generic<float>(ctx, (const float*)B.act, B.D, (float*)B.sraw, B.C, HW, 1, HW,
-                                                sb + SB_S_RAWSQ);
-        else
-          rc = launch_style_grad_generic<T>(ctx, (const T*)B.act, B.D, (T*)B.sraw, B.C, HW, B.C, 1, sb + SB_S_RAWSQ);
-        if (rc) return rc;
-      }
     }
-    inj[b].on = true;
-    inj[b].fc = c_on ? B.fc : nullptr;
-    inj[b].sraw = s_on ? B.sraw : nullptr;
-    inj[b].coef = sb + SB_C_COEF;          // [C_COEF, S_COEF, D_COEF] are consecutive
+    pl->inj[b].on = true;
+    pl->inj[b].fc = c_on ? B.fc : nullptr;
+    pl->inj[b].sraw = s_on ? B.sraw : nullptr;
+    pl->inj[b].coef = sb + SB_C_COEF;          // [C_COEF, S_COEF, D_COEF] are consecutive
+  }
+  pl->eval_phase = 1;
+  return 0;
+}
+
+template <typename T>
+static int eval_mid_impl(st2_plan* pl) {
+  st2_ctx* ctx = pl->ctx;
+  if (pl->eval_phase != 1) return st2_fail(ctx, ST2_ERR_STATE, "st2_eval_mid: call st2_eval_begin first");
+  const EvalSpec& es = pl->es;
+  const int want_grad = pl->eval_want_grad;
+  int rc = 0;
+  for (int k = 0; k < es.n; ++k) {
+    const int b = es.order[k];
+    Blob& B = pl->b[b];
+    if (!host_w_on(B.sw)) continue;
+    double* sb = pl->scal + b * ST2_SCAL_PER_BLOB;
+    double* raw_sum = pl->strip ? pl->red + 3 * b + 2 : sb + SB_S_RAWSQ;
+    const long long HW = (long long)B.H * B.W;
+    if (pl->strip) {
+      ProfScope ps(ctx, 3);
+      if ((rc = launch_gram_from_sum(ctx, pl->gram_red + pl->gram_red_off[b], B.gram_target, B.D, B.C,
+                                     (double)B.Hg * B.W, sb + SB_S_GRAMSQ)))
+        return rc;
+    }
+    ProfScope ps(ctx, 4);
+    if (want_grad) {
+      if (b == 0) {
+        rc = launch_style_grad_generic<float>(ctx, (const float*)B.act, B.D, (float*)B.sraw, B.C, HW, 1, HW, raw_sum);
+      } else if (pl->prec == ST2_PREC_FP16 && g_blobs[b].kind == KIND_CONV && B.C % 64 == 0) {
+        if ((rc = ensure(ctx, (void**)&B.Dh, sizeof(__half) * B.C * B.C))) return rc;
+        if (!B.tc_style &&
+            (rc = tc_conv_plan_create(ctx, (const __half*)B.act, B.Dh, B.H, B.W, B.C, B.C, 1, &B.tc_style)))
+          return rc;
+        style_scale_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(B.D, B.Dh, B.C, sb);
+        ST2_LAUNCH_CHECK(ctx);
+        rc = tc_conv_launch(ctx, B.tc_style, nullptr, nullptr, (__half*)B.sraw, EPI_RAW, 1.f, raw_sum);
+      } else {
+        rc = launch_style_grad_generic<T>(ctx, (const T*)B.act, B.D, (T*)B.sraw, B.C, HW, B.C, 1, raw_sum);
+      }
+    } else {
+      // loss-only evaluation still freezes the style normaliser (worker.py:265-266), which needs |D F|
+      if (b == 0)
+        rc = launch_style_grad_generic<float>(ctx, (const float*)B.act, B.D, (float*)B.sraw, B.C, HW, 1, HW, raw_sum);
+      else
+        rc = launch_style_grad_generic<T>(ctx, (const T*)B.act, B.D, (T*)B.sraw, B.C, HW, B.C, 1, raw_sum);
+    }
+    if (rc) return rc;
+  }
+  pl->eval_phase = 2;
+  return 0;
+}
+
+template <typename T>
+static int eval_end_impl(st2_plan* pl, float* grad_out) {
+  st2_ctx* ctx = pl->ctx;
+  if (pl->eval_phase != 2) return st2_fail(ctx, ST2_ERR_STATE, "st2_eval_end: call st2_eval_mid first");
+  const EvalSpec& es = pl->es;
+  const float* x = pl->eval_x;
+  int rc = 0;
+  if (pl->strip) {
+    scatter_sums_kernel<<<1, 32, 0, ctx->stream>>>(pl->red, pl->scal);
+    ST2_LAUNCH_CHECK(ctx);
   }
   if (es.n > 0) {
     ProfScope ps(ctx, 5);
@@ -419,21 +717,37 @@ static int eval_impl(st2_plan* pl, const float* x, float* grad_out, int want_gra
     ST2_LAUNCH_CHECK(ctx);
   }
   double* gscal = pl->scal + ST2_SCAL_GLOBAL_BASE;
-  if (want_grad) {
+  float* bwd = nullptr;
+  if (pl->eval_want_grad) {
     if (!grad_out) return st2_fail(ctx, ST2_ERR_ARG, "st2_eval: grad_dev is null");
     if (es.n > 0) {
-      if ((rc = backward_impl<T>(pl, top, inj, pl->bwd))) return rc;
+      if ((rc = backward_impl<T>(pl, pl->eval_top, pl->inj, pl->bwd))) return rc;
     } else {
       ST2_CUDA(ctx, cudaMemsetAsync(pl->bwd, 0, sizeof(float) * pl->b[0].n(), ctx->stream));
     }
-    ProfScope ps(ctx, 6);
-    rc = st2_pixel_terms(ctx, x, pl->bwd, grad_out, 3, pl->H, pl->W, pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
+    bwd = pl->bwd;
   } else {
-    rc = st2_pixel_terms(ctx, x, nullptr, nullptr, 3, pl->H, pl->W, pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
+    grad_out = nullptr;
+  }
+  {
+    ProfScope ps(ctx, 6);
+    if (pl->strip)
+      rc = pixel_terms_strip(ctx, pl->xp + pl->W, (long long)(pl->H + 2) * pl->W, 0, bwd, grad_out, 3, pl->H, pl->W,
+                             pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
+    else
+      rc = st2_pixel_terms(ctx, x, bwd, grad_out, 3, pl->H, pl->W, pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
   }
   if (rc) return rc;
-  final_kernel<<<1, 32, 0, ctx->stream>>>(es, pl->scal);
+  pl->eval_phase = 3;
+  return 0;
+}
+
+static int eval_final_impl(st2_plan* pl) {
+  st2_ctx* ctx = pl->ctx;
+  if (pl->eval_phase != 3) return st2_fail(ctx, ST2_ERR_STATE, "st2_eval_final: call st2_eval_end first");
+  final_kernel<<<1, 32, 0, ctx->stream>>>(pl->es, pl->scal, pl->strip ? &reinterpret_cast<SlabHeader*>(pl->slab)->err : nullptr);
   ST2_LAUNCH_CHECK(ctx);
+  pl->eval_phase = 0;
   return 0;
 }
 
@@ -455,6 +769,11 @@ int st2_ctx_create(int device, st2_ctx** out) {
   if (prop.major != 10)
     return st2_fail(nullptr, ST2_ERR_CUDA, "device %d is sm_%d%d; libst2 is built for sm_100a only", device,
                     prop.major, prop.minor);
+  for (const void* fn : st2_kernel_registry()) {          // load every kernel now (see st2_common.cuh)
+    cudaFuncAttributes attr;
+    if ((e = cudaFuncGetAttributes(&attr, fn)) != cudaSuccess)
+      return st2_fail(nullptr, ST2_ERR_CUDA, "loading the sm_100a kernels failed: %s", cudaGetErrorString(e));
+  }
   st2_ctx* ctx = new st2_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
@@ -543,20 +862,39 @@ int st2_set_conv_weights(st2_ctx* ctx, int ci, const float* w, const float* b, i
   return 0;
 }
 
-int st2_plan_create(st2_ctx* ctx, int H, int W, int prec, st2_plan** out) {
-  if (!ctx || !out || H < 1 || W < 1 || (prec != ST2_PREC_FP32 && prec != ST2_PREC_FP16))
-    return st2_fail(ctx, ST2_ERR_ARG, "st2_plan_create: bad arguments");
+static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, int rank, int world, int row0,
+                              int H_total, st2_plan** out) {
   st2_plan* pl = new st2_plan();
   pl->ctx = ctx; pl->H = H; pl->W = W; pl->prec = prec;
   pl->esz = prec == ST2_PREC_FP16 ? 2 : 4;
-  int h = H, w = W;
+  pl->strip = strip; pl->rank = rank; pl->world = world; pl->row0 = row0; pl->H_total = H_total;
+  pl->edge_top = (rank == 0); pl->edge_bot = (rank == world - 1);
+  if (strip) {
+    pl->lay = strip_layout(H, W, pl->esz);
+    ST2_CUDA(ctx, cudaMalloc(&pl->slab, pl->lay.total));
+    // halo rows at the canvas edges are never written: they stay zero = the convolutions' zero pad
+    ST2_CUDA(ctx, cudaMemsetAsync(pl->slab, 0, pl->lay.total, ctx->stream));
+    pl->xp = reinterpret_cast<float*>(pl->slab + pl->lay.xp_off);
+    ST2_CUDA(ctx, cudaMalloc(&pl->red, sizeof(double) * 3 * ST2_NUM_BLOBS));
+    long long gtot = 0;
+    for (int i = 0; i < ST2_NUM_BLOBS; ++i) gtot += (long long)g_blobs[i].channels * g_blobs[i].channels;
+    ST2_CUDA(ctx, cudaMalloc(&pl->gram_red, sizeof(float) * gtot));
+  }
+  int h = H, w = W, hg = H_total;
   for (int i = 0; i < ST2_NUM_BLOBS; ++i) {
-    if (g_blobs[i].kind == KIND_POOL) { h = pool_extent(h); w = pool_extent(w); }
-    pl->b[i].C = g_blobs[i].channels; pl->b[i].H = h; pl->b[i].W = w;
+    if (g_blobs[i].kind == KIND_POOL) { h = pool_extent(h); w = pool_extent(w); hg = pool_extent(hg); }
+    Blob& B = pl->b[i];
+    B.C = g_blobs[i].channels; B.H = h; B.W = w; B.Hg = hg;
     pl->order[i] = i;
-    if (i > 0) {
-      ST2_CUDA(ctx, cudaMalloc(&pl->b[i].act, pl->esz * pl->b[i].n()));
-      ST2_CUDA(ctx, cudaMalloc(&pl->b[i].grad, pl->esz * pl->b[i].n()));
+    if (i == 0) continue;
+    if (strip) {
+      B.act_pad = pl->slab + pl->lay.act_off[i];
+      B.grad_pad = pl->slab + pl->lay.grad_off[i];
+      B.act = (unsigned char*)B.act_pad + pl->lay.row_bytes[i];
+      B.grad = (unsigned char*)B.grad_pad + pl->lay.row_bytes[i];
+    } else {
+      ST2_CUDA(ctx, cudaMalloc(&B.act, pl->esz * B.n()));
+      ST2_CUDA(ctx, cudaMalloc(&B.grad, pl->esz * B.n()));
     }
   }
   pl->order_n = ST2_NUM_BLOBS;
@@ -565,15 +903,18 @@ int st2_plan_create(st2_ctx* ctx, int H, int W, int prec, st2_plan** out) {
   ST2_CUDA(ctx, cudaMalloc(&pl->gram_acc, sizeof(double) * 512 * 512));
   ST2_CUDA(ctx, cudaMalloc(&pl->bwd, sizeof(float) * pl->b[0].n()));
   if (prec == ST2_PREC_FP16) {
+    const int halo = strip ? 1 : 0;
     for (int i = 2; i < ST2_NUM_BLOBS; ++i) {
       if (g_blobs[i].kind != KIND_CONV) continue;
       const int ci = g_blobs[i].conv_index;
       if (!ctx->wh_fwd[ci]) return st2_fail(ctx, ST2_ERR_STATE, "load weights before creating an fp16 plan");
       Blob& cur = pl->b[i];
       Blob& below = pl->b[i - 1];
-      int rc = tc_conv_plan_create(ctx, (const __half*)below.act, ctx->wh_fwd[ci], cur.H, cur.W, below.C, cur.C, 9, &cur.tc_fwd);
+      int rc = tc_conv_plan_create(ctx, (const __half*)(strip ? below.act_pad : below.act), ctx->wh_fwd[ci], cur.H, cur.W,
+                                   below.C, cur.C, 9, &cur.tc_fwd, halo);
       if (rc) return rc;
-      rc = tc_conv_plan_create(ctx, (const __half*)cur.grad, ctx->wh_bwd[ci], cur.H, cur.W, cur.C, below.C, 9, &cur.tc_bwd);
+      rc = tc_conv_plan_create(ctx, (const __half*)(strip ? cur.grad_pad : cur.grad), ctx->wh_bwd[ci], cur.H, cur.W, cur.C,
+                               below.C, 9, &cur.tc_bwd, halo);
       if (rc) return rc;
     }
   }
@@ -581,15 +922,84 @@ int st2_plan_create(st2_ctx* ctx, int H, int W, int prec, st2_plan** out) {
   return 0;
 }
 
+int st2_plan_create(st2_ctx* ctx, int H, int W, int prec, st2_plan** out) {
+  if (!ctx || !out || H < 1 || W < 1 || (prec != ST2_PREC_FP32 && prec != ST2_PREC_FP16))
+    return st2_fail(ctx, ST2_ERR_ARG, "st2_plan_create: bad arguments");
+  return plan_create_common(ctx, H, W, prec, false, 0, 1, 0, H, out);
+}
+
+int st2_strip_plan_create(st2_ctx* ctx, int H_total, int W, int row0, int row1, int rank, int world, int prec,
+                          st2_plan** out) {
+  if (!ctx || !out || H_total < 1 || W < 1 || world < 1 || rank < 0 || rank >= world || row0 < 0 || row1 <= row0 ||
+      row1 > H_total || (prec != ST2_PREC_FP32 && prec != ST2_PREC_FP16))
+    return st2_fail(ctx, ST2_ERR_ARG, "st2_strip_plan_create: bad arguments");
+  // strips start on multiples of 16 rows so that all four 2x2/2 pools above a strip stay inside it
+  if (row0 % 16 || (rank != world - 1 && row1 % 16) || (rank == 0 && row0 != 0) || (rank == world - 1 && row1 != H_total))
+    return st2_fail(ctx, ST2_ERR_ARG, "st2_strip_plan_create: strip [%d, %d) of %d rows is not 16-row aligned", row0, row1,
+                    H_total);
+  return plan_create_common(ctx, row1 - row0, W, prec, true, rank, world, row0, H_total, out);
+}
+
+int st2_strip_ipc_handle(st2_plan* pl, void* handle_out) {
+  if (!pl || !pl->strip || !handle_out) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_strip_ipc_handle: not a strip plan");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ST2_IPC_HANDLE_BYTES, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  ST2_CUDA(pl->ctx, cudaIpcGetMemHandle(&h, pl->slab));
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int st2_strip_attach(st2_plan* pl, int side, const void* ipc_handle, st2_plan* local_peer, int peer_rows) {
+  if (!pl || !pl->strip || side < 0 || side > 1 || (!ipc_handle == !local_peer) || peer_rows < 1)
+    return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_strip_attach: bad arguments");
+  st2_ctx* ctx = pl->ctx;
+  if (pl->peer[side] && pl->peer_ipc[side]) cudaIpcCloseMemHandle(pl->peer[side]);
+  pl->peer[side] = nullptr;
+  if (local_peer) {
+    if (!local_peer->strip || local_peer->H != peer_rows || local_peer->W != pl->W || local_peer->esz != pl->esz)
+      return st2_fail(ctx, ST2_ERR_ARG, "st2_strip_attach: local peer does not match");
+    pl->peer[side] = local_peer->slab;
+    pl->peer_ipc[side] = false;
+  } else {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    void* p = nullptr;
+    ST2_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    pl->peer[side] = (unsigned char*)p;
+    pl->peer_ipc[side] = true;
+  }
+  pl->peer_lay[side] = strip_layout(peer_rows, pl->W, pl->esz);
+  return 0;
+}
+
+int st2_strip_reduce_block(st2_plan* pl, int which, void** dev_out, long long* count_out) {
+  if (!pl || !pl->strip || !dev_out || !count_out || which < 0 || which > 2)
+    return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_strip_reduce_block: bad arguments");
+  if (which == 0) { *dev_out = pl->gram_red; *count_out = pl->gram_red_used; }
+  else if (which == 1) { *dev_out = pl->red; *count_out = 3 * ST2_NUM_BLOBS; }
+  else { *dev_out = pl->scal + ST2_SCAL_GLOBAL_BASE + ST2_G_TV_NORM; *count_out = 6; }
+  return 0;
+}
+
+int st2_strip_halo_error(st2_plan* pl, int* err_out) {
+  if (!pl || !pl->strip || !err_out) return ST2_ERR_ARG;
+  ST2_CUDA(pl->ctx, cudaStreamSynchronize(pl->ctx->stream));
+  ST2_CUDA(pl->ctx, cudaMemcpy(err_out, &reinterpret_cast<SlabHeader*>(pl->slab)->err, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 void st2_plan_destroy(st2_plan* pl) {
   if (!pl) return;
+  for (int side = 0; side < 2; ++side)
+    if (pl->peer[side] && pl->peer_ipc[side]) cudaIpcCloseMemHandle(pl->peer[side]);
   for (int i = 0; i < ST2_NUM_BLOBS; ++i) {
     Blob& B = pl->b[i];
-    if (i > 0) { cudaFree(B.act); cudaFree(B.grad); }
+    if (i > 0 && !pl->strip) { cudaFree(B.act); cudaFree(B.grad); }
     cudaFree(B.fc); cudaFree(B.sraw); cudaFree(B.inj); cudaFree(B.gram_target); cudaFree(B.D); cudaFree(B.Dh);
     tc_conv_plan_destroy(B.tc_fwd); tc_conv_plan_destroy(B.tc_bwd); tc_conv_plan_destroy(B.tc_style);
     tc_gram_plan_destroy(B.tc_gram);
   }
+  cudaFree(pl->slab); cudaFree(pl->red); cudaFree(pl->gram_red);
   cudaFree(pl->scal); cudaFree(pl->gram_acc); cudaFree(pl->bwd);
   delete pl;
 }
@@ -659,6 +1069,7 @@ int st2_blob_export(st2_plan* pl, int blob, float* out) {
 int st2_backward(st2_plan* pl, int n, const int* blobs, const float* const* diffs, float* grad_out) {
   if (!pl || n < 1 || !blobs || !diffs || !grad_out) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_backward: bad arguments");
   st2_ctx* ctx = pl->ctx;
+  if (pl->strip) return st2_fail(ctx, ST2_ERR_UNSUPPORTED, "st2_backward: not available on row strips (use st2_eval_*)");
   Inject inj[ST2_NUM_BLOBS];
   int top = 0;
   for (int k = 0; k < n; ++k) {
@@ -698,6 +1109,8 @@ int st2_capture_content(st2_plan* pl, int blob) {
 int st2_gram(st2_plan* pl, int blob, float* out) {
   if (!pl || !out || blob < 0 || blob >= ST2_NUM_BLOBS) return ST2_ERR_ARG;
   if (blob > pl->top_cur) return st2_fail(pl->ctx, ST2_ERR_STATE, "%s not computed by the last forward", g_blobs[blob].name);
+  if (pl->strip)     /* un-normalised Gram sum of this strip: the caller all-reduces and divides by C*H_total*W */
+    return pl->prec == ST2_PREC_FP16 ? gram_sum_of_blob<__half>(pl, blob, out) : gram_sum_of_blob<float>(pl, blob, out);
   return pl->prec == ST2_PREC_FP16 ? gram_of_blob<__half>(pl, blob, nullptr, out, nullptr)
                                    : gram_of_blob<float>(pl, blob, nullptr, out, nullptr);
 }
@@ -751,10 +1164,32 @@ int st2_set_norm(st2_plan* pl, int kind, int blob, double value) {
   return 0;
 }
 
+int st2_eval_begin(st2_plan* pl, const float* x, int want_grad) {
+  if (!pl || !x) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_eval_begin: bad arguments");
+  return pl->prec == ST2_PREC_FP16 ? eval_begin_impl<__half>(pl, x, want_grad) : eval_begin_impl<float>(pl, x, want_grad);
+}
+
+int st2_eval_mid(st2_plan* pl) {
+  if (!pl) return ST2_ERR_ARG;
+  return pl->prec == ST2_PREC_FP16 ? eval_mid_impl<__half>(pl) : eval_mid_impl<float>(pl);
+}
+
+int st2_eval_end(st2_plan* pl, float* grad) {
+  if (!pl) return ST2_ERR_ARG;
+  return pl->prec == ST2_PREC_FP16 ? eval_end_impl<__half>(pl, grad) : eval_end_impl<float>(pl, grad);
+}
+
+int st2_eval_final(st2_plan* pl) { return pl ? eval_final_impl(pl) : ST2_ERR_ARG; }
+
 int st2_eval(st2_plan* pl, const float* x, float* grad, int want_grad) {
   if (!pl || !x) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_eval: bad arguments");
-  return pl->prec == ST2_PREC_FP16 ? eval_impl<__half>(pl, x, grad, want_grad)
-                                   : eval_impl<float>(pl, x, grad, want_grad);
+  if (pl->strip && pl->world > 1)
+    return st2_fail(pl->ctx, ST2_ERR_STATE, "st2_eval on a row strip: use st2_eval_begin/mid/end/final with all-reduces");
+  int rc = st2_eval_begin(pl, x, want_grad);
+  if (!rc) rc = st2_eval_mid(pl);
+  if (!rc) rc = st2_eval_end(pl, grad);
+  if (!rc) rc = st2_eval_final(pl);
+  return rc;
 }
 
 int st2_read_scalars(st2_plan* pl, double* host_out) {
@@ -786,3 +1221,7 @@ int st2_gram_nchw(st2_ctx* ctx, const float* x, int C, long long HW, float* out)
 }
 
 }  // extern "C"
+
+static St2KernelReg g_reg_net({ST2_KFN(halo_push_kernel), ST2_KFN(halo_wait_kernel), ST2_KFN(pack_x_kernel),
+                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(scatter_sums_kernel),
+                                  ST2_KFN(coef_kernel), ST2_KFN(final_kernel), ST2_KFN(pack_weights_kernel)});

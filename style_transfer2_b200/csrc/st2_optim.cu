@@ -101,3 +101,5 @@ int st2_axpy(st2_ctx* ctx, float alpha, const float* x, float* y, long long n) {
 }
 
 }  // extern "C"
+
+static St2KernelReg g_reg_optim({ST2_KFN(adam_kernel), ST2_KFN(dot_kernel), ST2_KFN(axpy_kernel)});

@@ -45,8 +45,11 @@ __device__ __forceinline__ float ipow(float m, int k) {
 //   p_norm = sum |v|^p (the 1/p is applied by the caller); p_grad = sign(v)|v|^(p-1)
 //   grad = bwd + tv*tv_grad + p*p_grad
 __global__ void pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd,
-                                   float* __restrict__ grad, int C, int H, int W, float tv, float beta,
-                                   float pw, float pp, float divisor, double* scal) {
+                                   float* __restrict__ grad, int C, int H, int W, long long xps, int wrap,
+                                   float tv, float beta, float pw, float pp, float divisor, double* scal) {
+  // x: row 0 of plane 0, planes xps floats apart.  wrap = 1: rows wrap around inside the tensor (whole
+  // canvas); wrap = 0: rows -1 and H are addressable halo rows (a row strip; the strips at the canvas
+  // edges hold the circular neighbours there).  bwd / grad are dense C x H x W.
   const long long HW = (long long)H * W, total = HW * C;
   const float half_beta = beta * 0.5f;
   const int m_norm = (half_beta == 1.0f) ? 1 : 2;
@@ -60,9 +63,9 @@ __global__ void pixel_terms_kernel(const float* __restrict__ x, const float* __r
     const int c = (int)(i / HW);
     const long long r = i - (long long)c * HW;
     const int h = (int)(r / W), w = (int)(r - (long long)h * W);
-    const float* xp = x + (long long)c * HW;
+    const float* xp = x + (long long)c * xps;
     const int wr = (w + 1 == W) ? 0 : w + 1, wl = (w == 0) ? W - 1 : w - 1;
-    const int hd = (h + 1 == H) ? 0 : h + 1, hu = (h == 0) ? H - 1 : h - 1;
+    const int hd = (wrap && h + 1 == H) ? 0 : h + 1, hu = (wrap && h == 0) ? H - 1 : h - 1;
     const float v = xp[(long long)h * W + w] / divisor;
     const float vr = xp[(long long)h * W + wr] / divisor;
     const float vl = xp[(long long)h * W + wl] / divisor;
@@ -175,15 +178,21 @@ inline int ew_grid(long long n, int sm_count) {
 
 }  // namespace
 
+int pixel_terms_strip(st2_ctx* ctx, const float* x, long long xps, int wrap, const float* bwd, float* grad_out,
+                      int C, int H, int W, float tv, float tv_power, float p, float p_power, float divisor,
+                      double* scal) {
+  if (!ctx || !x || !scal || C < 1 || H < 1 || W < 1) return st2_fail(ctx, ST2_ERR_ARG, "st2_pixel_terms: bad arguments");
+  pixel_terms_kernel<<<ew_grid((long long)C * H * W, ctx->sm_count), kThreads, 0, ctx->stream>>>(
+      x, bwd, grad_out, C, H, W, xps, wrap, tv, tv_power, p, p_power, divisor, scal);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 extern "C" {
 
 int st2_pixel_terms(st2_ctx* ctx, const float* x, const float* bwd, float* grad_out, int C, int H, int W,
                     float tv, float tv_power, float p, float p_power, float divisor, double* scal) {
-  if (!ctx || !x || !scal || C < 1 || H < 1 || W < 1) return st2_fail(ctx, ST2_ERR_ARG, "st2_pixel_terms: bad arguments");
-  pixel_terms_kernel<<<ew_grid((long long)C * H * W, ctx->sm_count), kThreads, 0, ctx->stream>>>(
-      x, bwd, grad_out, C, H, W, tv, tv_power, p, p_power, divisor, scal);
-  ST2_LAUNCH_CHECK(ctx);
-  return 0;
+  return pixel_terms_strip(ctx, x, (long long)H * W, 1, bwd, grad_out, C, H, W, tv, tv_power, p, p_power, divisor, scal);
 }
 
 int st2_preprocess_u8(st2_ctx* ctx, const unsigned char* hwc, float* nchw, int h, int w) {
@@ -247,3 +256,6 @@ int st2_resample(st2_ctx* ctx, const float* src, int planes, int h_in, int w_in,
 }
 
 }  // extern "C"
+
+static St2KernelReg g_reg_pixel({ST2_KFN(pixel_terms_kernel), ST2_KFN(preprocess_kernel<unsigned char>),
+                                    ST2_KFN(preprocess_kernel<float>), ST2_KFN(deprocess_kernel), ST2_KFN(resample_axis_kernel)});

@@ -1,0 +1,472 @@
+"""One large canvas split into row strips over several B200s (BASELINE config 4).
+
+The reference holds the whole image in one ``caffe.Net`` (worker.py:84-86) and caps its size
+(``max_size``, app.py:183-185); this module is the tiling scheduler that replaces that cap.  It
+mirrors the part of ``worker.StyleTransfer`` (worker.py:117-315) that a job needs --
+``set_input / set_content / set_style / set_weights / reset / opfunc / step`` -- for a canvas whose
+rows are partitioned over ``world`` strips:
+
+* every strip owns rows ``[row0, row1)`` (boundaries at multiples of 16 rows, ``parallel.strip_bounds``)
+  of x, of the gradient, of the L-BFGS history / Adam moments and of every activation;
+* before each 3x3 convolution (forward and data-gradient) the strips swap ONE boundary row.  libst2
+  does that itself: a push kernel stores the row into the neighbour's halo row through peer memory
+  (CUDA IPC mapping -> NVLink) and raises a flag there, the consumer spins on its flag in a 1-thread
+  kernel.  No NCCL, no host synchronisation on the halo path;
+* what remains are four small sum all-reduces per iteration, issued here between the phases of the
+  evaluation: the strips' Gram sums (<= 2.4 MB), 3 sums per weighted blob, 6 pixel-space sums, and the
+  L-BFGS dot-product block (one all-reduce per step thanks to the compact form, st2_lbfgs.cu).
+
+Two ways to place the strips:
+* ``torch.distributed`` (one process per GPU, NCCL): each process holds the strip of its rank;
+* ``local_world=P``: P strips inside one process on one GPU, one CUDA stream each -- the same kernels
+  and the same flag protocol, used by the single-GPU parity tests.
+
+PyTorch supplies device memory, streams and the NCCL process group; nothing else.
+"""
+from collections import OrderedDict
+import ctypes as C
+import time
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.distributed as dist
+
+from . import _lib, optimizers, parallel, utils, vgg
+from .messages import SetOptimizer, SetWeights
+from .model import Plan, _ptr
+from .worker import EPS_W, LazyLoss, LazyTrace
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {'shape': (int(count),), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 2, 'strides': None}
+
+
+def dev_tensor(ptr, count, dtype, device):
+    typestr = {torch.float32: '<f4', torch.float64: '<f8'}[dtype]
+    if count == 0:
+        return torch.empty(0, dtype=dtype, device=device)
+    return torch.as_tensor(_DevView(ptr, count, typestr), device=device)
+
+
+class StripPlan(Plan):
+    """``model.Plan`` for one row strip (st2_strip_plan_create)."""
+
+    def __init__(self, engine, height_total, width, row0, row1, rank, world, precision):
+        self.engine, self.W = engine, int(width)
+        self.H = int(row1 - row0)
+        self.H_total, self.row0, self.row1, self.rank, self.world = int(height_total), int(row0), int(row1), rank, world
+        self.lib = engine.lib
+        handle = C.c_void_p()
+        _lib.check(engine.ctx, self.lib.st2_strip_plan_create(engine.ctx, self.H_total, self.W, self.row0, self.row1,
+                                                              rank, world, precision, C.byref(handle)),
+                   'st2_strip_plan_create')
+        self.handle = handle
+        self._scal_host = (C.c_double * _lib.SCAL_TOTAL)()
+
+    def ipc_handle(self):
+        buf = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        self._check(self.lib.st2_strip_ipc_handle(self.handle, buf), 'st2_strip_ipc_handle')
+        return bytes(buf)
+
+    def attach(self, side, peer_rows, ipc_handle=None, local_peer=None):
+        hb = (C.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(ipc_handle) if ipc_handle is not None else None
+        self._check(self.lib.st2_strip_attach(self.handle, side, hb, local_peer.handle if local_peer else None,
+                                              int(peer_rows)), 'st2_strip_attach')
+
+    def reduce_block(self, which):
+        ptr, n = C.c_void_p(), C.c_longlong()
+        self._check(self.lib.st2_strip_reduce_block(self.handle, which, C.byref(ptr), C.byref(n)),
+                    'st2_strip_reduce_block')
+        return dev_tensor(ptr.value or 0, n.value, torch.float32 if which == 0 else torch.float64, self.engine.device)
+
+    def eval_begin(self, x, want_grad):
+        self._check(self.lib.st2_eval_begin(self.handle, _ptr(x), 1 if want_grad else 0), 'st2_eval_begin')
+
+    def eval_mid(self):
+        self._check(self.lib.st2_eval_mid(self.handle), 'st2_eval_mid')
+
+    def eval_end(self, grad):
+        self._check(self.lib.st2_eval_end(self.handle, _ptr(grad)), 'st2_eval_end')
+
+    def eval_final(self):
+        self._check(self.lib.st2_eval_final(self.handle), 'st2_eval_final')
+
+    def halo_error(self):
+        err = C.c_int()
+        self._check(self.lib.st2_strip_halo_error(self.handle, C.byref(err)), 'st2_strip_halo_error')
+        return err.value
+
+
+class _Strip:
+    """Per-strip state held by this process."""
+
+    def __init__(self, rank, row0, row1):
+        self.rank, self.row0, self.row1 = rank, row0, row1
+        self.plan = None
+        self.stream = None
+        self.x = None
+        self.content = None
+        self.grads = [None, None]
+        self.turn = 0
+        self.opt = None                # st2_lbfgs handle
+        self.m1 = self.m2 = None       # Adam moments
+        self.grad = None               # gradient at x owned by the optimizer
+
+    @property
+    def rows(self):
+        return self.row1 - self.row0
+
+
+class TiledTransfer:
+    """Row-tiled ``StyleTransfer``.  All ranks call every method in the same order (SPMD)."""
+
+    def __init__(self, model, height, width, local_world=None, optimizer='lbfgs', step_size=None):
+        self.model, self.engine = model, model.engine
+        self.H, self.W = int(height), int(width)
+        self.dist = local_world is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if local_world is not None:
+            self.world, ranks = int(local_world), list(range(int(local_world)))
+        elif self.dist:
+            self.world, ranks = dist.get_world_size(), [dist.get_rank()]
+        else:
+            self.world, ranks = 1, [0]
+        bounds = parallel.strip_bounds(self.H, self.world)
+        if any(e <= s for s, e in bounds):
+            raise ValueError('canvas of %d rows is too small for %d strips of >= 16 rows' % (self.H, self.world))
+        self.bounds = bounds
+        dev = self.engine.device
+        self.strips = []
+        main = torch.cuda.current_stream(dev)
+        for r in ranks:
+            st = _Strip(r, *bounds[r])
+            st.stream = main if len(ranks) == 1 else torch.cuda.Stream(dev)
+            with torch.cuda.stream(st.stream):
+                self.engine.sync_stream()
+                st.plan = StripPlan(self.engine, self.H, self.W, st.row0, st.row1, r, self.world, model.precision)
+            self.strips.append(st)
+        torch.cuda.synchronize(dev)
+        self._attach()
+        self.weights = pd.DataFrame(np.ones((len(vgg.BLOBS), len(SetWeights.loss_names))), list(vgg.BLOBS),
+                                    SetWeights.loss_names, np.float32)
+        self.params = {w: 1 for w in SetWeights.scalar_loss_names}
+        self.optimizer_name = optimizer
+        self.step_size = SetOptimizer.step_sizes[optimizer] if step_size is None else step_size
+        self.b1, self.b2 = 0.9, 0.999
+        self.t = 0
+        self.traces = []
+        self.style = None
+        self._spec = []
+        self._weights_dirty = True
+        self._content_done, self._style_done = set(), set()
+        self._have_eval = False
+        self._cold = True
+        self._adam_items = 0
+        self.loss = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _each(self):
+        """Iterate the local strips with their stream current and libst2 pointed at it."""
+        for st in self.strips:
+            with torch.cuda.stream(st.stream):
+                self.engine.sync_stream()
+                yield st
+        self.engine.sync_stream()
+
+    def _attach(self):
+        """Circular neighbours: side 0 = the strip above (rank-1), side 1 = the strip below."""
+        rows = [e - s for s, e in self.bounds]
+        if self.dist:
+            me = self.strips[0]
+            handles = [None] * self.world
+            dist.all_gather_object(handles, me.plan.ipc_handle())
+            for side, peer in ((0, (me.rank - 1) % self.world), (1, (me.rank + 1) % self.world)):
+                if peer == me.rank:
+                    me.plan.attach(side, rows[peer], local_peer=me.plan)
+                else:
+                    me.plan.attach(side, rows[peer], ipc_handle=handles[peer])
+            dist.barrier()
+        else:
+            by_rank = {st.rank: st for st in self.strips}
+            for st in self.strips:
+                for side, peer in ((0, (st.rank - 1) % self.world), (1, (st.rank + 1) % self.world)):
+                    st.plan.attach(side, rows[peer], local_peer=by_rank[peer].plan)
+
+    def all_reduce(self, tensors):
+        """Sum ``tensors[i]`` (one per local strip) over all strips, in place, stream-ordered."""
+        if not tensors or tensors[0].numel() == 0:
+            return
+        if len(self.strips) > 1:
+            s0 = self.strips[0].stream
+            for st in self.strips[1:]:
+                s0.wait_event(st.stream.record_event())
+            with torch.cuda.stream(s0):
+                for t in tensors[1:]:
+                    tensors[0].add_(t)
+            done = s0.record_event()
+            for st, t in zip(self.strips[1:], tensors[1:]):
+                st.stream.wait_event(done)
+                with torch.cuda.stream(st.stream):
+                    t.copy_(tensors[0])
+        if self.dist:
+            with torch.cuda.stream(self.strips[0].stream):
+                dist.all_reduce(tensors[0])
+
+    def _rows_of(self, full, st):
+        """Rows of a (1, 3, H, W) device tensor that belong to strip ``st`` (contiguous copy)."""
+        return full[:, :, st.row0:st.row1, :].contiguous()
+
+    def _upload(self, image):
+        arr = np.asarray(image)
+        h, w = arr.shape[:2]
+        out = self.engine.empty(1, 3, h, w)
+        dev = torch.from_numpy(np.array(arr, copy=True)).to(self.engine.device)
+        fn = 'st2_preprocess_u8' if arr.dtype == np.uint8 else 'st2_preprocess_f32'
+        if arr.dtype != np.uint8:
+            dev = dev.float().contiguous()
+        self.engine.call(fn, C.c_void_p(dev.data_ptr()), C.c_void_p(out.data_ptr()), h, w)
+        return out
+
+    # ------------------------------------------------------------------ job set-up (worker.py:191-229)
+    def set_input(self, image):
+        full = self._upload(image)
+        if tuple(full.shape[2:]) != (self.H, self.W):
+            raise ValueError('input is %s, canvas is %s' % (tuple(full.shape[2:]), (self.H, self.W)))
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        for st in self._each():
+            st.x = self._rows_of(full, st)
+        self.reset()
+
+    def set_content(self, image):
+        full = self._upload(image)
+        if tuple(full.shape[2:]) != (self.H, self.W):
+            raise ValueError('content is %s, canvas is %s' % (tuple(full.shape[2:]), (self.H, self.W)))
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        for st in self._each():
+            st.content = self._rows_of(full, st)
+        self._content_done = set()
+        self.objective_changed()
+
+    def set_style(self, image):
+        self.style = self._upload(image)
+        self._style_done = set()
+        self.objective_changed()
+
+    def set_weights(self, weights, params):
+        self.weights = pd.DataFrame.from_dict(weights, dtype=np.float32)
+        self.params = params
+        self._weights_dirty = True
+        self.objective_changed()
+
+    def objective_changed(self):
+        """optimizers.py:42-46 / 121-125."""
+        self._have_eval = False
+        self.loss = None
+        if self.optimizer_name == 'lbfgs':
+            for st in self._each():
+                if st.opt is not None:
+                    self.engine.lib.st2_lbfgs_reset(st.opt)
+            self._cold = True
+        else:
+            self._adam_items = 0
+            for st in self.strips:
+                if st.m1 is not None:
+                    st.m1.zero_()
+
+    def reset(self):
+        """worker.py:172-175: new norms, t = 0, fresh optimizer state."""
+        for st in self._each():
+            st.plan.reset_norms()
+            if self.optimizer_name == 'lbfgs':
+                if st.opt is not None:
+                    self.engine.lib.st2_lbfgs_destroy(st.opt)
+                h = C.c_void_p()
+                self.engine.call('st2_lbfgs_create', st.x.numel(), 10, C.byref(h))
+                _lib.check(self.engine.ctx, self.engine.lib.st2_lbfgs_set_global_length(h, float(3 * self.H * self.W)),
+                           'st2_lbfgs_set_global_length')
+                st.opt = h
+            else:
+                st.m1 = torch.zeros_like(st.x)
+                st.m2 = torch.zeros_like(st.x)
+        self._cold = True
+        self._adam_items = self._adam_items2 = 0
+        self.t = 0
+        self._have_eval = False
+
+    def active_layers(self):
+        nonzeros = abs(self.weights) > EPS_W
+        return list(self.weights.index[abs(nonzeros.sum(axis=1)) > EPS_W])
+
+    def _sync_plans(self):
+        if self._weights_dirty:
+            spec, order = [], []
+            table = self.weights
+            rows = []
+            for name in self.active_layers():
+                b = vgg.BLOB_INDEX[name]
+                vals = [float(table[col][name]) if col in table.columns else 0.0 for col in SetWeights.loss_names]
+                vals = [0.0 if (np.isnan(v) or abs(v) <= EPS_W) else v for v in vals]
+                rows.append((b, vals))
+                order.append(b)
+                spec.append((b, vals[0] != 0.0, vals[1] != 0.0, vals[2] != 0.0))
+            for st in self._each():
+                for b in range(_lib.NUM_BLOBS):
+                    st.plan.set_blob_weights(b, 0.0, 0.0, 0.0)
+                for b, vals in rows:
+                    st.plan.set_blob_weights(b, *vals)
+                st.plan.set_eval_order(order)
+                st.plan.set_params(float(self.params['tv']), float(self.params['tv_power']), float(self.params['p']),
+                                   float(self.params['p_power']))
+            self._spec = spec
+            self._weights_dirty = False
+        need_c = [b for b, c_on, _, _ in self._spec if c_on and b not in self._content_done]
+        if need_c:
+            for st in self._each():
+                st.plan.forward(st.content, max(need_c))
+                for b in need_c:
+                    st.plan.capture_content(b)
+            self._content_done.update(need_c)
+        need_s = [b for b, _, s_on, _ in self._spec if s_on and b not in self._style_done]
+        if need_s:
+            # the style image has its own size: every process computes its Gram targets on a whole-canvas plan
+            hs, ws = self.style.shape[2:]
+            self.engine.sync_stream()
+            sp = Plan(self.engine, hs, ws, self.model.precision)
+            try:
+                sp.forward(self.style, max(need_s))
+                grams = {b: sp.gram(b) for b in need_s}
+                torch.cuda.current_stream(self.engine.device).synchronize()
+            finally:
+                sp.close()
+            for st in self._each():
+                for b in need_s:
+                    st.plan.set_style_gram(b, grams[b])
+            self._style_done.update(need_s)
+
+    # ------------------------------------------------------------------ objective (worker.py:231-301)
+    def opfunc(self, return_grad=True):
+        """Collective evaluation at the strips' current x.  Returns (loss, [grad per local strip])."""
+        self._sync_plans()
+        grads = []
+        for st in self._each():
+            if return_grad:
+                st.turn ^= 1
+                if st.grads[st.turn] is None:
+                    st.grads[st.turn] = torch.empty_like(st.x)
+                grads.append(st.grads[st.turn])
+            st.plan.eval_begin(st.x, return_grad)
+        self.all_reduce([st.plan.reduce_block(0) for st in self.strips])
+        for st in self._each():
+            st.plan.eval_mid()
+        self.all_reduce([st.plan.reduce_block(1) for st in self.strips])
+        for st, g in zip(self._each(), grads if return_grad else [None] * len(self.strips)):
+            st.plan.eval_end(g)
+        self.all_reduce([st.plan.reduce_block(2) for st in self.strips])
+        for st in self._each():
+            st.plan.eval_final()
+        st0 = self.strips[0]
+        host = torch.empty(_lib.SCAL_TOTAL, dtype=torch.float64, pin_memory=True)
+        with torch.cuda.stream(st0.stream):
+            self.engine.sync_stream()
+            st0.plan.copy_scalars_async(host)
+            ev = torch.cuda.Event()
+            ev.record(st0.stream)
+        self.engine.sync_stream()
+        tr = LazyTrace(host, ev, list(self._spec), return_grad, time.perf_counter())
+        tr.halo_timeout = lambda: bool(host[_lib.SCAL_GLOBAL_BASE + _lib.G_HALO_TIMEOUT] != 0.0)
+        self.traces.append(tr)
+        del self.traces[:-256]
+        return (LazyLoss(tr), grads) if return_grad else LazyLoss(tr)
+
+    # ------------------------------------------------------------------ optimizers (optimizers.py)
+    def _lbfgs_sums(self):
+        n = self.engine.lib.st2_lbfgs_sums_count()
+        return [dev_tensor(self.engine.lib.st2_lbfgs_sums_dev(st.opt), n, torch.float64, self.engine.device)
+                for st in self.strips]
+
+    def _lcall(self, st, name, *args):
+        _lib.check(self.engine.ctx, getattr(self.engine.lib, name)(st.opt, *args), name)
+
+    def _step_lbfgs(self):
+        """optimizers.py:62-77 on sharded vectors: one all-reduce of the dot-product block per step."""
+        if not self._have_eval:
+            self.loss, grads = self.opfunc()
+            for st, g in zip(self.strips, grads):
+                st.grad = g
+            self._have_eval = True
+        for st in self._each():
+            self._lcall(st, 'st2_lbfgs_advance_begin', _ptr(st.grad))
+        if self._cold:
+            self.all_reduce(self._lbfgs_sums())
+        for st in self._each():
+            self._lcall(st, 'st2_lbfgs_advance_end', _ptr(st.x), _ptr(st.grad), float(self.step_size))
+        loss, grads = self.opfunc()
+        for st, g in zip(self._each(), grads):
+            self._lcall(st, 'st2_lbfgs_commit_begin', _ptr(g), _ptr(st.grad))
+        self.all_reduce(self._lbfgs_sums())
+        for st, g in zip(self._each(), grads):
+            self._lcall(st, 'st2_lbfgs_commit_end')
+            st.grad = g
+        self._cold = False
+        self.loss = loss
+        return loss
+
+    def _step_adam(self):
+        """optimizers.py:20-27: purely element-wise, no reduction."""
+        loss, grads = self.opfunc()
+        self._adam_items += 1
+        self._adam_items2 = getattr(self, '_adam_items2', 0) + 1
+        for st, g in zip(self._each(), grads):
+            self.engine.call('st2_adam_step', _ptr(st.x), _ptr(g), _ptr(st.m1), _ptr(st.m2), st.x.numel(),
+                             float(self.step_size), self.b1, self.b2, self._adam_items, self._adam_items2)
+        self.loss = loss
+        return loss
+
+    def step(self, fetch=True):
+        """worker.py:303-310."""
+        self.t += 1
+        loss = self._step_lbfgs() if self.optimizer_name == 'lbfgs' else self._step_adam()
+        tr = self.traces[-1]
+        tr('fevals', self.t)
+        if not fetch:
+            return None, None
+        return self.image(), tr.data
+
+    # ------------------------------------------------------------------ results
+    def gather(self, per_strip):
+        """Full (1, 3, H, W) device tensor from per-local-strip row tensors (all ranks get it)."""
+        full = self.engine.zeros(1, 3, self.H, self.W)
+        main = torch.cuda.current_stream(self.engine.device)
+        for st, t in zip(self.strips, per_strip):
+            main.wait_event(st.stream.record_event())
+            full[:, :, st.row0:st.row1, :] = t
+        if self.dist:
+            dist.all_reduce(full)
+        return full
+
+    def image(self):
+        """Deprocessed iterate, HxWx3 fp32 host array (CaffeModel.deprocess, worker.py:68-71)."""
+        x = self.gather([st.x for st in self.strips])
+        hwc = self.engine.empty(self.H, self.W, 3)
+        self.engine.sync_stream()
+        self.engine.call('st2_deprocess', C.c_void_p(x.data_ptr()), C.c_void_p(hwc.data_ptr()), self.H, self.W)
+        return hwc.cpu().numpy()
+
+    def check(self):
+        """Raise if a halo wait ever timed out (a neighbouring strip died)."""
+        for st in self._each():
+            if st.plan.halo_error():
+                raise RuntimeError('strip %d: halo exchange timed out' % st.rank)
+
+    def close(self):
+        for st in self.strips:
+            if st.opt is not None:
+                self.engine.lib.st2_lbfgs_destroy(st.opt)
+                st.opt = None
+            if st.plan is not None:
+                st.plan.close()
+                st.plan = None

@@ -1,0 +1,140 @@
+"""Row-strip tiling of one canvas (BASELINE config 4) on a single GPU: P strips in one
+process (``TiledTransfer(local_world=P)``) run the same kernels, the same peer-memory halo pushes and
+the same flag protocol as the one-process-per-GPU deployment, so the split can be checked against the
+un-split plan (same arithmetic) and the CPU oracle on one device.  The multi-process / CUDA-IPC /
+NCCL leg is ``tools/tiled_check.py`` (run under torchrun on >= 2 GPUs).
+
+Tolerances: strips vs the un-split GPU plan differ only in summation order of the reductions
+(Gram sums, loss sums, L-BFGS dots): every trace value and the gradient within 2e-5 relative in
+fp32; 1e-3 / 2e-3 in fp16 (the fp16 copy of the Gram difference G-A re-rounds after a different
+fp32 summation order).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err, psnr
+
+pytestmark = pytest.mark.gpu
+
+WEIGHTS = {'content': {'conv4_2': 0.08}, 'style': {'conv1_1': 1, 'conv2_1': 1, 'conv3_1': 1, 'conv4_1': 1, 'conv5_1': 1},
+           'deepdream': {'pool2': 0.01}}
+PARAMS = {'p': 50, 'p_power': 6, 'tv': 5, 'tv_power': 2}
+
+
+@pytest.fixture(scope='module')
+def models():
+    from style_transfer2_b200.model import B200Model
+    from style_transfer2_b200 import utils
+    cache = {}
+
+    def get(precision):
+        if precision not in cache:
+            cache[precision] = B200Model(precision=precision)
+        utils.set_default_engine(cache[precision].engine)
+        return cache[precision]
+    return get
+
+
+def images(h, w, seed=0):
+    rs = np.random.RandomState(seed)
+    # smooth-ish images so that activations are not pure noise
+    def img(hh, ww):
+        base = rs.uniform(0, 255, (hh // 4 + 2, ww // 4 + 2, 3))
+        up = np.kron(base, np.ones((4, 4, 1)))[:hh, :ww]
+        return np.uint8(np.clip(up + rs.normal(0, 12, (hh, ww, 3)), 0, 255))
+    return img(h, w), img(h, w), img(h - 8, w + 16)
+
+
+def whole(model, x0, content, style, optimizer='lbfgs'):
+    from style_transfer2_b200 import optimizers
+    from style_transfer2_b200.worker import StyleTransfer
+    st = StyleTransfer(model)
+    if optimizer == 'adam':
+        st.optimizer_cls = optimizers.AdamOptimizer
+        st.step_size = 10
+    st.set_input(x0)
+    st.set_content(content)
+    st.set_style(style)
+    st.set_weights(WEIGHTS, PARAMS)
+    assert st.start()
+    return st
+
+
+def tiled(model, x0, content, style, world, optimizer='lbfgs'):
+    from style_transfer2_b200.tiled import TiledTransfer
+    tt = TiledTransfer(model, x0.shape[0], x0.shape[1], local_world=world, optimizer=optimizer)
+    tt.set_input(x0)
+    tt.set_content(content)
+    tt.set_style(style)
+    tt.set_weights(WEIGHTS, PARAMS)
+    return tt
+
+
+@pytest.mark.parametrize('precision,world,hw', [('fp32', 1, (64, 48)), ('fp32', 2, (64, 80)), ('fp32', 3, (100, 72)),
+                                                ('fp16', 2, (96, 80)), ('fp16', 4, (150, 131)), ('fp16', 1, (48, 64))])
+def test_strips_reproduce_the_whole_canvas_objective(models, precision, world, hw):
+    m = models(precision)
+    x0, content, style = images(*hw)
+    ref = whole(m, x0, content, style)
+    loss_ref, grad_ref = ref.opfunc(ref.input)
+    tr_ref = ref.traces[-1].data
+    tt = tiled(m, x0, content, style, world)
+    loss, grads = tt.opfunc()
+    tr = tt.traces[-1].data
+    tt.check()
+    grad = tt.gather(grads).cpu().numpy()
+    tol_s, tol_g = (2e-5, 2e-5) if precision == 'fp32' else (1e-3, 2e-3)
+    assert list(tr) == list(tr_ref)
+    for k, v in tr_ref.items():
+        if k == 'time':
+            continue
+        assert np.isclose(tr[k], v, rtol=tol_s), (k, tr[k], v)
+    assert rel_err(grad, grad_ref.cpu().numpy()) < tol_g
+    tt.close()
+
+
+def test_strips_match_the_cpu_oracle(models):
+    """Directly against the oracle (reference semantics), not only against our own whole-canvas plan."""
+    from oracle.caffe_cpu import CaffeCPUModel
+    from oracle.transfer import Transfer
+    m = models('fp32')
+    x0, content, style = images(64, 80)
+    o = Transfer(CaffeCPUModel())
+    o.set_input(x0)
+    o.set_content(content)
+    o.set_style(style)
+    o.set_weights(WEIGHTS, PARAMS)
+    assert o.start()
+    loss_o, grad_o = o.opfunc(o.input)
+    tt = tiled(m, x0, content, style, 2)
+    loss, grads = tt.opfunc()
+    assert abs(float(loss) - loss_o) / abs(loss_o) < 1e-4
+    assert rel_err(tt.gather(grads).cpu().numpy(), grad_o) < 2e-3
+    tt.close()
+
+
+@pytest.mark.parametrize('optimizer,steps,min_db', [('lbfgs', 4, 60.0), ('adam', 8, 60.0)])
+def test_strips_follow_the_whole_canvas_trajectory(models, optimizer, steps, min_db):
+    m = models('fp32')
+    x0, content, style = images(96, 64)
+    ref = whole(m, x0, content, style, optimizer)
+    tt = tiled(m, x0, content, style, 3, optimizer)
+    for i in range(steps):
+        img_ref, tr_ref = ref.step()
+        img, tr = tt.step()
+        assert tr['fevals'] == i + 1
+        assert psnr(img, img_ref) > min_db, (i, psnr(img, img_ref))
+        assert np.isclose(tr['loss'], tr_ref['loss'], rtol=1e-3)
+    tt.check()
+    tt.close()
+
+
+def test_strip_plan_rejects_misaligned_rows(models):
+    from style_transfer2_b200 import _lib
+    from style_transfer2_b200.tiled import StripPlan
+    m = models('fp32')
+    with pytest.raises(_lib.St2Error):
+        StripPlan(m.engine, 64, 32, 8, 64, 1, 2, m.precision)        # strip must start on a multiple of 16 rows
+    with pytest.raises(_lib.St2Error):
+        StripPlan(m.engine, 64, 32, 0, 24, 0, 2, m.precision)        # inner boundary not 16-aligned
