@@ -135,7 +135,12 @@ template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+// fp16 stores saturate: the reference's line-search-free L-BFGS overshoots by orders of magnitude for a
+// few steps (pixels at +-11 000) and recovers; an inf in an activation would instead
+// poison every later iterate with NaN.
+__device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ __half2 h2_sat(float a, float b) { return __floats2half2_rn(sat_h(a), sat_h(b)); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(sat_h(v)); }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int pool_extent(int n) { return n > 1 ? (n - 2 + 1) / 2 + 1 : 1; }   // ceil((n-2)/2)+1

@@ -251,7 +251,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint4 o;
             __half2* hp = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) hp[e] = __floats2half2_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
             op[q] = o;
           }
         }

@@ -21,7 +21,7 @@ template <> struct Vec16<__half> {
     uint4 u;
     __half2* hp = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) hp[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[2 * e], v[2 * e + 1]);
     *reinterpret_cast<uint4*>(p) = u;
   }
 };
