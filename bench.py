@@ -13,6 +13,10 @@ N > 1: one process per GPU (torchrun), every rank runs an independent job of the
 (job-level data parallelism, no data-path collective) -> weak scaling; value = all ranks' iterations
 / max-over-ranks device time.
 
+``--workload canvas`` (BASELINE config 4): ONE --size x --size canvas (default 4096) split into row
+strips over the N GPUs (style_transfer2_b200/tiled.py: halo rows over peer memory, four small NCCL
+all-reduces per iteration) -> strong scaling; value = iterations of the whole canvas per second.
+
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -149,12 +153,39 @@ def build_job(size, precision, seed_shift=0):
     return st
 
 
+class TiledJob:
+    """The same step()/input surface as StyleTransfer for one row-tiled canvas (this rank's strip)."""
+
+    def __init__(self, size, precision):
+        from style_transfer2_b200.model import B200Model
+        from style_transfer2_b200.tiled import TiledTransfer
+        content, style, x0 = load_images(size)
+        model = B200Model(gpu=int(os.environ.get('LOCAL_RANK', 0)), precision=precision)
+        self.tt = TiledTransfer(model, size, size)
+        self.tt.set_input(x0)
+        self.tt.set_content(content)
+        self.tt.set_style(style)
+        self.tt.set_weights(WEIGHTS, PARAMS)
+        self.engine = model.engine
+
+    @property
+    def input(self):
+        return self.tt.strips[0].x
+
+    def step(self, fetch=True):
+        self.tt.step(fetch=False)
+        if not fetch:
+            return None, None
+        return None, self.tt.traces[-1].data          # the iterate's rows are read back by the caller
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--size', type=int, default=1024)
+    ap.add_argument('--size', type=int, default=0)
+    ap.add_argument('--workload', default='jobs', choices=['jobs', 'canvas'])
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('ST2_PRECISION', 'fp16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -162,7 +193,8 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
-    size = args.size
+    canvas = args.workload == 'canvas'
+    size = args.size or (4096 if canvas else 1024)
     flops_conv = 2 * conv_flops(size, size)
     gram_flops = 0
     dims = [(size, size)]
@@ -170,9 +202,11 @@ def main():
         dims.append((pool_extent(dims[-1][0]), pool_extent(dims[-1][1])))
     for i, c in enumerate((64, 128, 256, 512, 512)):
         gram_flops += 4 * c * c * dims[i][0] * dims[i][1]
-    config = {'workload': 'config2: %dx%d canvas, style conv1_1..conv5_1 + content conv4_2, tv/p, L-BFGS m=10' % (size, size),
+    config = {'workload': ('config4: one %dx%d canvas in row strips, ' if canvas else 'config2: %dx%d canvas, ') % (size, size) +
+                          'style conv1_1..conv5_1 + content conv4_2, tv/p, L-BFGS m=10',
               'canvas': [size, size], 'optimizer': 'lbfgs', 'precision': args.precision,
-              'parallelism': 'independent jobs x%d' % world if world > 1 else 'single job',
+              'parallelism': ('row strips x%d (halo rows over peer memory, 4 all-reduces/iteration)' % world) if canvas
+                             else ('independent jobs x%d' % world if world > 1 else 'single job'),
               'l2': 'working set (>=1.3 GB activations + 0.25 GB L-BFGS history per iteration) exceeds the 126 MB L2',
               'algorithmic_tflop_per_iteration': round((flops_conv + gram_flops) / 1e12, 4)}
 
@@ -202,8 +236,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    st = build_job(size, args.precision, seed_shift=rank)
+    st = TiledJob(size, args.precision) if canvas else build_job(size, args.precision, seed_shift=rank)
     eng = st.engine
+    jobs = 1 if canvas else world                 # whole-job units per step
     # ---- device-resident arm: `value`
     for _ in range(max(args.warmup, 3)):
         st.step(fetch=False)
@@ -225,7 +260,7 @@ def main():
         t = torch.tensor([ms], device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * args.steps / (ms / 1000.0)
+    value = jobs * args.steps / (ms / 1000.0)
 
     # ---- end-to-end arm: the optimizer seam with HOST parameters.  Every step uploads x from
     # pinned host memory, steps, and reads the iterate (HxWx3 fp32) plus the trace back.
@@ -251,9 +286,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     nbytes = st.input.numel() * 4
-    e2e = {'value': world * args.steps / (ms_e2e / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': nbytes,
-           'd2h_bytes_per_step': 2 * nbytes + 8 * 560,
-           'note': 'x uploaded from pinned host memory every step; iterate image + x + trace block read back'}
+    if canvas:
+        e2e = {'value': args.steps / (ms_e2e / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': nbytes * world,
+               'd2h_bytes_per_step': (nbytes + 8 * 560) * world,
+               'note': 'every rank uploads its strip of x from pinned host memory every step and reads the new strip + trace block back'}
+    else:
+        e2e = {'value': world * args.steps / (ms_e2e / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': nbytes,
+               'd2h_bytes_per_step': 2 * nbytes + 8 * 560,
+               'note': 'x uploaded from pinned host memory every step; iterate image + x + trace block read back'}
 
     # ---- per-category device time (CUDA events on the launch stream) for the roofline
     import ctypes as C
@@ -276,18 +316,32 @@ def main():
     roofline = None
     key = 'conv_tc' if 'conv_tc' in cats else ('conv_exact' if 'conv_exact' in cats else None)
     if key:
-        fl = 2 * conv_flops(size, size, first=1)              # conv1_2..conv5_1, fwd + dgrad (conv1_1 is its own kernel)
+        fl = 2 * conv_flops(size, size, first=1) // (world if canvas else 1)   # conv1_2..conv5_1, fwd + dgrad, this GPU's share
         t_s = cats[key]['ms_per_step'] / 1000.0
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
         ach = fl / t_s / 1e12
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture of one
+        # iteration (profiles/*_tcconv_traffic.json, made by profiles/ncu_traffic.py); 1024^2 workload only
+        traffic, traffic_src = None, None
+        if key == 'conv_tc' and size == 1024 and not canvas:
+            import glob
+            found = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_tcconv_traffic.json')))
+            if found:
+                tj = json.load(open(found[-1]))
+                traffic, traffic_src = tj['conv3x3_dram_bytes_per_launch'], os.path.relpath(found[-1], ROOT)
+        n_launch = cats[key]['launch_spans_per_step']
         roofline = {'kernel': 'tc_conv_kernel (tcgen05 implicit GEMM, fwd + dgrad, 24 launches/iteration)' if key == 'conv_tc' else 'conv_exact_kernel',
                     'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                    'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s (of fallback)',
+                    'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
+                    'traffic_source': traffic_src, 'launches_per_step': n_launch,
+                    'flops_per_launch': fl / n_launch if n_launch else None,
+                    'avg_launch_ms': cats[key]['ms_per_step'] / n_launch if n_launch else None,
+                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s (of fallback)',
                     'flops_per_step': fl, 'ms_per_step': cats[key]['ms_per_step']}
 
     line = {'metric': 'style-transfer iterations/sec', 'value': value, 'unit': 'it/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'higher_is_better': True, 'scaling': 'strong' if canvas else 'weak', 'vs_baseline': None,
             'dtype': 'f16 operands / f32 accumulate' if args.precision == 'fp16' else 'f32',
             'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
             'roofline': roofline, 'kernel_time_ms_per_step': cats}

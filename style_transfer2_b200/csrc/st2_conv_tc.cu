@@ -73,7 +73,8 @@ template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
-               __half* __restrict__ out, const int epi, const float out_scale, double* sumsq) {
+               __half* __restrict__ out, const int epi, const float out_scale, double* sumsq,
+               const TcInject inj) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by SWIZZLE_128B operand tiles
@@ -191,6 +192,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float ss = 0.f;
     int local = 0;
     const int row_h = row / g.TW, row_w = row % g.TW;
+    // loss injection fused into the data-gradient epilogue (worker.py:249-277 diffs added below the ReLU mask)
+    float cc = 0.f, sc = 0.f, dc = 0.f;
+    if (inj.coef != nullptr) { cc = (float)inj.coef[0]; sc = (float)inj.coef[1]; dc = (float)inj.coef[2]; }
     TileWalk tk;
     tk.init(g, blockIdx.x);
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local, tk.next(g)) {
@@ -235,6 +239,36 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const float2 f = __half22float2(hp[e]);
                 if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
                 if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
+              }
+              if (inj.coef != nullptr) {
+                if (inj.fc != nullptr) {
+                  const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(inj.fc + obase + c * 32) + q);
+                  const __half2* cp = reinterpret_cast<const __half2*>(&c4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(hp[e]), t = __half22float2(cp[e]);
+                    v[8 * q + 2 * e] = fmaf(cc, f.x - t.x, v[8 * q + 2 * e]);
+                    v[8 * q + 2 * e + 1] = fmaf(cc, f.y - t.y, v[8 * q + 2 * e + 1]);
+                  }
+                }
+                if (inj.sraw != nullptr) {
+                  const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32) + q);
+                  const __half2* sp = reinterpret_cast<const __half2*>(&s4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 t = __half22float2(sp[e]);
+                    v[8 * q + 2 * e] = fmaf(sc, t.x, v[8 * q + 2 * e]);
+                    v[8 * q + 2 * e + 1] = fmaf(sc, t.y, v[8 * q + 2 * e + 1]);
+                  }
+                }
+                if (dc != 0.f) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(hp[e]);
+                    v[8 * q + 2 * e] = fmaf(dc, f.x, v[8 * q + 2 * e]);
+                    v[8 * q + 2 * e + 1] = fmaf(dc, f.y, v[8 * q + 2 * e + 1]);
+                  }
+                }
               }
             }
           } else {
@@ -372,7 +406,7 @@ void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
 
 template <int BN>
 static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
-                     float out_scale, double* sumsq) {
+                     float out_scale, double* sumsq, const TcInject& inj) {
   static bool attr_set = false;
   if (!attr_set) {
     ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -385,19 +419,25 @@ static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   p->g.step_tw = (grid / p->g.n_blocks) % p->g.tiles_w;
   p->g.step_th = (grid / p->g.n_blocks) / p->g.tiles_w;
   tc_conv_kernel<BN><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias,
-                                                                              act, out, epi, out_scale, sumsq);
+                                                                              act, out, epi, out_scale, sumsq, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
-                   float out_scale, double* sumsq) {
+                   float out_scale, double* sumsq, const TcInject* inj_in) {
   if (epi == EPI_BIAS_RELU && !bias) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: bias required");
   if (epi == EPI_MASK && !act) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: act required");
+  TcInject inj;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr;
+  if (inj_in) {
+    if (epi != EPI_MASK) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: injection needs the mask epilogue");
+    inj = *inj_in;
+  }
   switch (p->bn) {
-    case 256: return launch_bn<256>(ctx, p, bias, act, out, epi, out_scale, sumsq);
-    case 128: return launch_bn<128>(ctx, p, bias, act, out, epi, out_scale, sumsq);
-    default:  return launch_bn<64>(ctx, p, bias, act, out, epi, out_scale, sumsq);
+    case 256: return launch_bn<256>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
+    case 128: return launch_bn<128>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
+    default:  return launch_bn<64>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
   }
 }
 

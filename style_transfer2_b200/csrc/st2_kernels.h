@@ -77,8 +77,11 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
                         int cout, int taps, TcConvPlan** out, int halo = 0);
 void tc_conv_plan_destroy(TcConvPlan* p);
 // epi per EPI_*; bias fp32 (EPI_BIAS_RELU); act fp16 NHWC (EPI_MASK); sumsq nullable (sum of fp32 outputs^2)
+// inj (EPI_MASK only): out = mask(acc) + coef[0] (act - fc) + coef[1] sraw + coef[2] act -- the loss diffs of
+// the blob below enter under its ReLU mask in the same pass (fc / sraw nullable; coef: 3 device doubles)
+struct TcInject { const __half* fc; const __half* sraw; const double* coef; };
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
-                   float out_scale, double* sumsq);
+                   float out_scale, double* sumsq, const TcInject* inj = nullptr);
 // Gram partials with tcgen05 (MN-major operands): Gd += F^T F for fp16 NHWC features
 struct TcGramPlan;
 int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGramPlan** out);

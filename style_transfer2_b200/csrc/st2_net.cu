@@ -477,13 +477,16 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
   if (top == 0) {
     ST2_CUDA(ctx, cudaMemsetAsync(grad_out, 0, sizeof(float) * pl->b[0].n(), ctx->stream));
   }
+  bool fused_inj = false;      // the injection of blob i was already applied by the data-gradient epilogue above it
   for (int i = top; i >= 1; --i) {
     Blob& cur = pl->b[i];
     Blob& below = pl->b[i - 1];
     const bool have_above = (i < top);
     const bool is_conv = g_blobs[i].kind == KIND_CONV;
     int rc = 0;
-    if (inj[i].on) {
+    if (inj[i].on && fused_inj) {
+      fused_inj = false;
+    } else if (inj[i].on) {
       CombineArgs a;
       a.gin = have_above ? cur.grad : nullptr;
       a.act = cur.act; a.fc = inj[i].fc; a.sraw = inj[i].sraw; a.out = cur.grad; a.n = cur.n();
@@ -509,6 +512,12 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
       } else if (pl->prec == ST2_PREC_FP32) {
         rc = launch_conv_exact(ctx, (const float*)cur.grad, ctx->wf32_bwd[ci], nullptr, (const float*)below.act,
                                (float*)below.grad, cur.H, cur.W, cur.C, below.C, mask_below ? EPI_MASK : EPI_RAW, lo, hi);
+      } else if (below_conv && inj[i - 1].on && inj[i - 1].coef != nullptr && !getenv("ST2_NO_FUSED_INJECT")) {
+        TcInject ti;
+        ti.fc = (const __half*)inj[i - 1].fc; ti.sraw = (const __half*)inj[i - 1].sraw; ti.coef = inj[i - 1].coef;
+        rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad, EPI_MASK, 1.f,
+                            nullptr, &ti);
+        fused_inj = true;
       } else {
         rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad,
                             mask_below ? EPI_MASK : EPI_RAW, 1.f, nullptr);
