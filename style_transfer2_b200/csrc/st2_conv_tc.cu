@@ -69,6 +69,87 @@ struct TileWalk {
   }
 };
 
+// One 32-channel chunk of one output pixel: accumulator -> bias+ReLU | ReLU mask (+ loss injection) | raw
+// -> fp16 (saturating) -> four 16-byte stores.  a4 / s4: the pixel's 32 channels of the mask source and
+// of the style-gradient injection, already in registers.
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi, const float* __restrict__ bias_c,
+                                          const uint4 (&a4)[4], const uint4 (&s4)[4], const __half* __restrict__ fc_c,
+                                          const bool have_inj, const bool have_s, const float cc, const float sc,
+                                          const float dc, const float out_scale, const bool want_ss, float& ss,
+                                          __half* __restrict__ out_c) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (epi == EPI_BIAS_RELU) {
+    const float4* bp = reinterpret_cast<const float4*>(bias_c);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(bp + q);
+      v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x, 0.f);
+      v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y, 0.f);
+      v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z, 0.f);
+      v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w, 0.f);
+    }
+  } else if (epi == EPI_MASK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __half2* hp = reinterpret_cast<const __half2*>(&a4[q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(hp[e]);
+        if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
+        if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
+      }
+      if (have_inj) {
+        // loss diffs of the blob below enter under its ReLU mask (worker.py:100-102)
+        if (fc_c != nullptr) {
+          const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(fc_c) + q);
+          const __half2* cp = reinterpret_cast<const __half2*>(&c4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hp[e]), t = __half22float2(cp[e]);
+            v[8 * q + 2 * e] = fmaf(cc, f.x - t.x, v[8 * q + 2 * e]);
+            v[8 * q + 2 * e + 1] = fmaf(cc, f.y - t.y, v[8 * q + 2 * e + 1]);
+          }
+        }
+        if (have_s) {
+          const __half2* sp = reinterpret_cast<const __half2*>(&s4[q]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(sp[e]);
+            v[8 * q + 2 * e] = fmaf(sc, t.x, v[8 * q + 2 * e]);
+            v[8 * q + 2 * e + 1] = fmaf(sc, t.y, v[8 * q + 2 * e + 1]);
+          }
+        }
+        if (dc != 0.f) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hp[e]);
+            v[8 * q + 2 * e] = fmaf(dc, f.x, v[8 * q + 2 * e]);
+            v[8 * q + 2 * e + 1] = fmaf(dc, f.y, v[8 * q + 2 * e + 1]);
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= out_scale;
+    if (want_ss) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(out_c);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    __half2* hp = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+    op[q] = o;
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -195,6 +276,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // loss injection fused into the data-gradient epilogue (worker.py:249-277 diffs added below the ReLU mask)
     float cc = 0.f, sc = 0.f, dc = 0.f;
     if (inj.coef != nullptr) { cc = (float)inj.coef[0]; sc = (float)inj.coef[1]; dc = (float)inj.coef[2]; }
+    constexpr int NCH = BN / 32;
+    constexpr bool PF = (BN <= 128);
+    const bool masked = (epi == EPI_MASK);
+    const bool have_inj = masked && inj.coef != nullptr;
+    const bool have_s = have_inj && inj.sraw != nullptr;
     TileWalk tk;
     tk.init(g, blockIdx.x);
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++local, tk.next(g)) {
@@ -205,88 +291,62 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int w = tk.tw * g.TW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      // Operands of the epilogue that do not depend on the accumulator (ReLU-mask source, style-gradient
+      // injection) are fetched BEFORE waiting for the MMAs of this tile on the narrow tiles: those layers
+      // are memory-bound and a DRAM round trip per 32-channel chunk would otherwise serialise behind the wait.
+      uint4 pa[PF ? NCH : 1][4], ps[PF ? NCH : 1][4];
+      if (PF) {
+        if (valid && masked) {
+          const uint4* ap = reinterpret_cast<const uint4*>(act + obase);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pa[c][q] = __ldg(ap + c * 4 + q);
+        }
+        if (valid && have_s) {
+          const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ps[c][q] = __ldg(sp + c * 4 + q);
+        }
+      }
       if (lane == 0) tc::mbar_wait(&tmem_full[acc], acc_phase);     // one poller per warp
       __syncwarp();
       tc::fence_after_sync();
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+      if (PF) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(t_row + c * 32, r);
+          tc::tmem_ld_wait();
+          if (valid)
+            epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
+                      (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                      out_scale, sumsq != nullptr, ss, out + obase + c * 32);
+        }
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(t_row + c * 32, r);
-        tc::tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(t_row + c * 32, r);
+          tc::tmem_ld_wait();
+          if (valid) {
+            uint4 a4[4], s4[4];
+            if (masked) {
+              const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (epi == EPI_BIAS_RELU) {
-            const float4* bp = reinterpret_cast<const float4*>(bias + nb * BN + c * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b = __ldg(bp + q);
-              v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x, 0.f);
-              v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y, 0.f);
-              v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z, 0.f);
-              v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w, 0.f);
+              for (int q = 0; q < 4; ++q) a4[q] = __ldg(ap + q);
             }
-          } else if (epi == EPI_MASK) {
-            const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
+            if (have_s) {
+              const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 a = __ldg(ap + q);
-              const __half2* hp = reinterpret_cast<const __half2*>(&a);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(hp[e]);
-                if (!(f.x > 0.f)) v[8 * q + 2 * e] = 0.f;
-                if (!(f.y > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
-              }
-              if (inj.coef != nullptr) {
-                if (inj.fc != nullptr) {
-                  const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(inj.fc + obase + c * 32) + q);
-                  const __half2* cp = reinterpret_cast<const __half2*>(&c4);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(hp[e]), t = __half22float2(cp[e]);
-                    v[8 * q + 2 * e] = fmaf(cc, f.x - t.x, v[8 * q + 2 * e]);
-                    v[8 * q + 2 * e + 1] = fmaf(cc, f.y - t.y, v[8 * q + 2 * e + 1]);
-                  }
-                }
-                if (inj.sraw != nullptr) {
-                  const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32) + q);
-                  const __half2* sp = reinterpret_cast<const __half2*>(&s4);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 t = __half22float2(sp[e]);
-                    v[8 * q + 2 * e] = fmaf(sc, t.x, v[8 * q + 2 * e]);
-                    v[8 * q + 2 * e + 1] = fmaf(sc, t.y, v[8 * q + 2 * e + 1]);
-                  }
-                }
-                if (dc != 0.f) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(hp[e]);
-                    v[8 * q + 2 * e] = fmaf(dc, f.x, v[8 * q + 2 * e]);
-                    v[8 * q + 2 * e + 1] = fmaf(dc, f.y, v[8 * q + 2 * e + 1]);
-                  }
-                }
-              }
+              for (int q = 0; q < 4; ++q) s4[q] = __ldg(sp + q);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= out_scale;
-            if (sumsq != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
-            }
-          }
-          uint4* op = reinterpret_cast<uint4*>(out + obase + c * 32);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            __half2* hp = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-            op[q] = o;
+            epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
+                      (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                      out_scale, sumsq != nullptr, ss, out + obase + c * 32);
           }
         }
       }
