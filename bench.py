@@ -185,7 +185,8 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--size', type=int, default=0)
-    ap.add_argument('--workload', default='jobs', choices=['jobs', 'canvas'])
+    ap.add_argument('--workload', default='jobs', choices=['jobs', 'canvas', 'serving'])
+    ap.add_argument('--jobs', type=int, default=64, help='serving: number of independent jobs')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('ST2_PRECISION', 'fp16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -235,6 +236,41 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.workload == 'serving':
+        # BASELINE config 5: --jobs independent 512 x 512 jobs fed as message sequences to the job scheduler,
+        # sharded over the ranks (job j -> rank j % world), --steps iterations each.
+        from style_transfer2_b200 import parallel, serving
+        from style_transfer2_b200.model import B200Model
+        ssize = args.size or 512
+        content, style, _ = load_images(ssize)
+        jobs = [serving.job_messages(ssize, content, style, WEIGHTS, PARAMS, seed=j) for j in range(args.jobs)]
+        model = B200Model(gpu=local, precision=args.precision)
+        sched = serving.JobScheduler(model, max_resident=8)
+        sched.run(jobs[:world], max(args.warmup, 3), world, rank, fetch_final=False)        # warm-up: one job per rank
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = sched.run(jobs, args.steps, world, rank, fetch_final=True)
+        e1.record()
+        barrier()
+        ms = parallel.all_max(e0.elapsed_time(e1), device='cuda')
+        lat = [v['latency_s'] for part in parallel.gather_objects({k: {'latency_s': v['latency_s']} for k, v in out.items()})
+               for v in part.values()]
+        if rank == 0:
+            total = args.jobs * args.steps
+            print(json.dumps({'metric': 'style-transfer iterations/sec', 'value': total / (ms / 1000.0), 'unit': 'it/s',
+                              'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                              'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+                              'vs_baseline': None, 'dtype': 'f16 operands / f32 accumulate' if args.precision == 'fp16' else 'f32',
+                              'data': 'synthetic',
+                              'config': {'workload': 'config5: %d independent %dx%d jobs (message sequences) through the job scheduler, %d L-BFGS iterations each, final iterate fetched' % (args.jobs, ssize, ssize, args.steps),
+                                         'parallelism': 'job j -> rank j %% %d, <= 8 resident per GPU, round-robin stepping' % world},
+                              'job_latency_s': {'median': statistics.median(lat), 'max': max(lat)},
+                              'gpu_launches': model.engine.launches()}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     st = TiledJob(size, args.precision) if canvas else build_job(size, args.precision, seed_shift=rank)
     eng = st.engine

@@ -55,6 +55,25 @@ class Engine:
                                                b.ctypes.data_as(C.c_void_p), w.shape[0], w.shape[1])
             _lib.check(self.ctx, rc, 'st2_set_conv_weights(%s)' % name)
 
+    def trace_slot(self, owner):
+        """A row of pinned host memory for one evaluation's scalar block.  Rows come from a ring
+        allocated once (cudaHostAlloc costs ~1 ms, far too much per iteration); when the ring wraps, the
+        previous owner of a row is told to move its data out first (``owner.detach()``)."""
+        if getattr(self, '_ring', None) is None:
+            self._ring = torch.empty((128, _lib.SCAL_TOTAL), dtype=torch.float64, pin_memory=True)
+            self._ring_owner = [None] * self._ring.shape[0]
+            self._ring_next = 0
+        i = self._ring_next
+        self._ring_next = (i + 1) % self._ring.shape[0]
+        prev = self._ring_owner[i]
+        if prev is not None:
+            prev = prev()
+            if prev is not None:
+                prev.detach()
+        import weakref
+        self._ring_owner[i] = weakref.ref(owner)
+        return self._ring[i]
+
     def launches(self):
         return int(self.lib.st2_launch_count(self.ctx))
 
@@ -179,6 +198,7 @@ class B200Model:
         self.gpu = gpu
         self._params = params
         self._plans = OrderedDict()
+        self._free_plans = {}            # (H, W) -> idle plans handed back by finished jobs (serving)
         self._last_plan = None
         logger.info('Initializing the B200 engine (%s).', precision)
         self.reload_net()
@@ -197,6 +217,10 @@ class B200Model:
         for plan in self._plans.values():
             plan.close()
         self._plans.clear()
+        for plans in self._free_plans.values():
+            for plan in plans:
+                plan.close()
+        self._free_plans.clear()
         self.engine = Engine(self.gpu, params)
 
     # -- worker.py:63-71 (host versions, identical arithmetic)
@@ -222,6 +246,25 @@ class B200Model:
                 old.close()
         self._plans[key] = plan
         return plan
+
+    def acquire_plan(self, height, width):
+        """A plan owned by the caller until ``release_plan``.  Creating / destroying a plan costs ~50
+        synchronising cudaMalloc / cudaFree calls, so a serving process recycles them: a recycled plan keeps
+        its buffers, the next owner resets norms, weights and targets."""
+        free = self._free_plans.get((int(height), int(width)))
+        if free:
+            return free.pop()
+        return Plan(self.engine, int(height), int(width), self.precision)
+
+    def release_plan(self, plan, keep=12):
+        if plan is None or not plan.handle:
+            return
+        bucket = self._free_plans.setdefault((plan.H, plan.W), [])
+        if sum(len(v) for v in self._free_plans.values()) >= keep:
+            torch.cuda.current_stream(self.engine.device).synchronize()
+            plan.close()
+        else:
+            bucket.append(plan)
 
     # -- worker.py:77-86
     def forward(self, image, layers=None):

@@ -369,15 +369,15 @@ class TiledTransfer:
         for st in self._each():
             st.plan.eval_final()
         st0 = self.strips[0]
-        host = torch.empty(_lib.SCAL_TOTAL, dtype=torch.float64, pin_memory=True)
+        tr = LazyTrace(None, None, list(self._spec), return_grad, time.perf_counter())
+        tr._host = host = self.engine.trace_slot(tr)
         with torch.cuda.stream(st0.stream):
             self.engine.sync_stream()
             st0.plan.copy_scalars_async(host)
-            ev = torch.cuda.Event()
+            tr._event = ev = torch.cuda.Event()
             ev.record(st0.stream)
         self.engine.sync_stream()
-        tr = LazyTrace(host, ev, list(self._spec), return_grad, time.perf_counter())
-        tr.halo_timeout = lambda: bool(host[_lib.SCAL_GLOBAL_BASE + _lib.G_HALO_TIMEOUT] != 0.0)
+        tr.halo_timeout = lambda tr=tr: bool(tr._host[_lib.SCAL_GLOBAL_BASE + _lib.G_HALO_TIMEOUT] != 0.0)
         self.traces.append(tr)
         del self.traces[:-256]
         return (LazyLoss(tr), grads) if return_grad else LazyLoss(tr)

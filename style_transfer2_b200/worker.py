@@ -44,6 +44,7 @@ class LazyTrace:
 
     def __init__(self, host_block, event, spec, want_grad, when):
         self._host, self._event, self._spec = host_block, event, spec
+        self._detached = False
         self._want_grad, self._when = want_grad, when
         self._data = None
         self._extra = []
@@ -54,6 +55,13 @@ class LazyTrace:
         else:
             self._put(name, value)
         return value
+
+    def detach(self):
+        """Move the scalar block out of the shared pinned ring (its row is about to be reused)."""
+        if not self._detached and self._host is not None:
+            self._event.synchronize()
+            self._host = self._host.clone()
+            self._detached = True
 
     def _put(self, name, value):
         while name in self._data:
@@ -141,9 +149,12 @@ class StyleTransfer:
 
     TRACE_KEEP = 256
 
-    def __init__(self, model):
+    def __init__(self, model, private_plans=False):
         self.model = model
         self.engine = model.engine
+        # Plans carry per-job state (content/style targets, frozen normalisers).  The reference runs one job
+        # per worker process; several jobs resident on one GPU (serving.JobScheduler) each need their own.
+        self._private_plans = {} if private_plans else None
         utils.set_default_engine(self.engine)
         self.is_running = False
         self.is_starting = False
@@ -333,7 +344,15 @@ class StyleTransfer:
 
     def _sync_plan(self):
         h, w = self.input.shape[2:]
-        plan = self.model.plan(h, w)
+        if self._private_plans is None:
+            plan = self.model.plan(h, w)
+        else:
+            plan = self._private_plans.get((h, w))
+            if plan is None:
+                for old in self._private_plans.values():
+                    self.model.release_plan(old)
+                self._private_plans.clear()
+                plan = self._private_plans[(h, w)] = self.model.acquire_plan(h, w)
         if plan is not self._plan:
             if self._plan is not None and self._plan.handle and not getattr(self, '_norms_reset', False):
                 for kind, table in self.norms.items():          # norms survive a scale change
@@ -376,7 +395,7 @@ class StyleTransfer:
         need_s = [b for b, _, s_on, _ in self._spec if s_on and b not in self._style_done]
         if need_s:
             hs, ws = self.style.shape[2:]
-            sp = plan if (hs, ws) == (h, w) else Plan(self.engine, hs, ws, self.model.precision)
+            sp = plan if (hs, ws) == (h, w) else self.model.acquire_plan(hs, ws)
             try:
                 sp.forward(self.style, max(need_s))
                 for b in need_s:
@@ -384,8 +403,7 @@ class StyleTransfer:
                     self._style_done.add(b)
             finally:
                 if sp is not plan:
-                    torch.cuda.current_stream(self.engine.device).synchronize()
-                    sp.close()
+                    self.model.release_plan(sp, keep=4 if self._private_plans is None else 12)
         return plan
 
     def _next_grad(self):
@@ -403,11 +421,11 @@ class StyleTransfer:
         plan = self._sync_plan()
         grad = self._next_grad() if return_grad else None
         plan.eval(x, grad, return_grad)
-        host = torch.empty(_lib.SCAL_TOTAL, dtype=torch.float64, pin_memory=True)
+        tr = LazyTrace(None, None, list(self._spec), return_grad, time.perf_counter())
+        tr._host = host = self.engine.trace_slot(tr)
         plan.copy_scalars_async(host)
-        ev = torch.cuda.Event()
+        tr._event = ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.engine.device))
-        tr = LazyTrace(host, ev, list(self._spec), return_grad, time.perf_counter())
         self.traces.append(tr)
         self._norm_source = tr
         if len(self.traces) > self.TRACE_KEEP:
@@ -426,6 +444,14 @@ class StyleTransfer:
         if not fetch:
             return None, None
         return self.image(x), tr.data
+
+    def close(self):
+        """Release the plans this job owns (private_plans=True)."""
+        if self._private_plans:
+            for plan in self._private_plans.values():
+                self.model.release_plan(plan)
+            self._private_plans.clear()
+        self._plan = None
 
     def write_trace(self, filename):
         df = pd.DataFrame(t.data for t in self.traces)

@@ -313,6 +313,41 @@ def test_config1_hundred_lbfgs_steps_stay_finite_and_land_where_the_reference_do
     assert db > 15.0
 
 
+@pytest.mark.parametrize('precision,min_psnr', [('fp32', 45.0), ('fp16', 33.0)])
+def test_config3_multiscale_adam_follows_the_oracle(golden, models, precision, min_psnr):
+    """BASELINE config 3 in miniature: Adam (step 10), three stages joined by the worker's
+    SetImages(size, RESAMPLE, RESAMPLE) path (worker.py:154-170, optimizers.py:29-40): x and the first moment
+    Lanczos-resampled, the second moment bilinear + clamp, normalisers persist across stages.  The oracle runs
+    the same message sequence on the CPU."""
+    from oracle.caffe_cpu import CaffeCPUModel
+    from oracle.transfer import Transfer, Adam
+    g = golden('small')
+    weights, params = ast.literal_eval(str(g['weights_repr'])), ast.literal_eval(str(g['params_repr']))
+    ora = Transfer(CaffeCPUModel())
+    ora.optimizer_cls, ora.step_size = Adam, 10
+    ora.set_input(g['x0'])
+    ora.set_content(g['content'])
+    ora.set_style(g['style'])
+    ora.set_weights(weights, params)
+    assert ora.start()
+    st = _transfer(g, models(precision), 'adam')
+    h, w = g['x0'].shape[:2]
+    for stage, size in enumerate(((h, w), (int(h * 1.4), int(w * 1.4)), (h * 2, w * 2))):
+        if stage:
+            for t in (ora, st):
+                t.resample_input(size)
+                t.resample_content(size)
+            assert tuple(st.input.shape[2:]) == size
+            assert st.norms['s'].keys() == ora.norms['s'].keys()            # frozen normalisers survive the resize
+            for k, v in ora.norms['s'].items():
+                assert np.isclose(st.norms['s'][k], v, rtol=2e-3), (k, st.norms['s'][k], v)
+        for _ in range(5):
+            img_o, tr_o = ora.step()
+            img, tr = st.step()
+        assert psnr(img, img_o) > min_psnr, (stage, psnr(img, img_o))
+        assert np.isclose(tr['loss'], tr_o['loss'], rtol=1e-3 if precision == 'fp32' else 2e-2), (stage, tr['loss'], tr_o['loss'])
+
+
 def test_gram_matrix_device(models):
     from style_transfer2_b200.worker import gram_matrix
     from oracle.transfer import gram

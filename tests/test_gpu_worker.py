@@ -93,3 +93,40 @@ def test_worker_speaks_the_reference_protocol(golden):
     finally:
         app_in.close(0)
         app_out.close(0)
+
+
+def test_job_scheduler_runs_interleaved_jobs_like_standalone_ones(golden):
+    """BASELINE config 5 in miniature: five jobs (different seeds, two canvas sizes, one on Adam) resident on
+    one GPU and stepped round-robin give what each job gives when run alone through StyleTransfer."""
+    import ast
+    from style_transfer2_b200 import optimizers, serving
+    from style_transfer2_b200.model import B200Model
+    from style_transfer2_b200.worker import StyleTransfer
+    g = golden('small')
+    weights, params = ast.literal_eval(str(g['weights_repr'])), ast.literal_eval(str(g['params_repr']))
+    model = B200Model(precision='fp32')
+    h, w = g['x0'].shape[:2]
+    jobs, specs = [], []
+    for j in range(5):
+        size = (h, w) if j % 2 == 0 else (h - 16, w - 16)
+        content = g['content'][:size[0], :size[1]]
+        opt = 'adam' if j == 3 else 'lbfgs'
+        jobs.append(serving.job_messages(size, content, g['style'], weights, params, optimizer=opt, seed=j))
+        specs.append((size, content, opt))
+    out = serving.JobScheduler(model, max_resident=3).run(jobs, steps=3)
+    assert sorted(out) == list(range(5))
+    for j, (size, content, opt) in enumerate(specs):
+        st = StyleTransfer(model)
+        if opt == 'adam':
+            st.optimizer_cls, st.step_size = optimizers.AdamOptimizer, 10
+        st.set_input(np.uint8(np.random.RandomState(j).uniform(0, 255, size + (3,))))
+        st.set_content(content)
+        st.set_style(g['style'])
+        st.set_weights(weights, params)
+        assert st.start()
+        for _ in range(3):
+            img, tr = st.step()
+        it = out[j]['iterate']
+        assert it.i == 3 and out[j]['steps'] == 3 and out[j]['latency_s'] > 0
+        assert np.abs(np.float32(it.image) - img).max() < 1e-2 * max(1.0, np.abs(img).max())
+        assert np.isclose(it.trace['loss'], tr['loss'], rtol=1e-5)
