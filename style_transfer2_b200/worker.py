@@ -144,6 +144,20 @@ class LazyLoss:
         return format(float(self), spec)
 
 
+class IterateHandle:
+    """An iterate on its way to the host (``StyleTransfer.step_async``): the deprocessed image is copied
+    device -> pinned host on a side stream while the next iteration computes.  ``result()`` waits for the
+    copy and returns ``(image, trace)`` exactly as ``step()`` does.  The image array is a view of a
+    double-buffered pinned block: consume (or copy) it before the second-next ``step_async``."""
+
+    def __init__(self, host, done, trace, t):
+        self._host, self._done, self.trace, self.t = host, done, trace, t
+
+    def result(self):
+        self._done.synchronize()
+        return self._host.numpy(), self.trace.data
+
+
 class StyleTransfer:
     """worker.py:117-315 with device-resident state."""
 
@@ -231,6 +245,32 @@ class StyleTransfer:
         host.copy_(hwc, non_blocking=True)
         torch.cuda.current_stream(self.engine.device).synchronize()
         return host.numpy()
+
+    def image_async(self, x, trace):
+        """Enqueue deprocess + device->host copy of ``x`` on the download stream; no host wait."""
+        dev = self.engine.device
+        main = torch.cuda.current_stream(dev)
+        h, w = x.shape[2:]
+        if getattr(self, '_dl', None) is None or self._dl['shape'] != (h, w):
+            self._dl = {'shape': (h, w), 'stream': torch.cuda.Stream(dev), 'turn': 0,
+                        'dev': [self.engine.empty(h, w, 3) for _ in range(2)],
+                        'host': [torch.empty((h, w, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)],
+                        'done': [None, None]}
+        d = self._dl
+        d['turn'] ^= 1
+        k = d['turn']
+        if d['done'][k] is not None:
+            main.wait_event(d['done'][k])              # the slot's previous copy must have left the device buffer
+        self.engine.call('st2_deprocess', C.c_void_p(x.data_ptr()), C.c_void_p(d['dev'][k].data_ptr()), h, w)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(d['stream']):
+            d['stream'].wait_event(ready)
+            d['host'][k].copy_(d['dev'][k], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(d['stream'])
+        d['done'][k] = done
+        return IterateHandle(d['host'][k], done, trace, self.t)
 
     def _pinned_buffer(self, shape):
         for buf in self._pinned:
@@ -453,6 +493,16 @@ class StyleTransfer:
             self._private_plans.clear()
         self._plan = None
 
+    def step_async(self):
+        """``step()`` without the host wait: returns an ``IterateHandle``.  Lets the caller overlap the
+        iterate's trip to the host (12.6 MB at 1024^2) and its own pickling / sending with the next iteration
+        (SURVEY 8f #3: the reference pickles every iterate synchronously, worker.py:351-353)."""
+        self.t += 1
+        x, _ = self.optimizer.step()
+        tr = self.traces[-1]
+        tr('fevals', self.t)
+        return self.image_async(x, tr)
+
     def write_trace(self, filename):
         df = pd.DataFrame(t.data for t in self.traces)
         df.index.name = 'step'
@@ -495,18 +545,37 @@ class Worker:
                     except zmq.ZMQError:
                         if self.transfer.is_running:
                             if self.transfer.check_consistency():
-                                image, trace = self.transfer.step()
-                                self.sock_out.send_pyobj(Iterate(np.array(image), self.transfer.t, dict(trace)))
+                                # one iterate stays in flight: iteration t+1 is enqueued before iterate t is
+                                # waited for, pickled and sent, so the transport overlaps the compute
+                                handle = self.transfer.step_async()
+                                self._flush()
+                                self._pending = handle
                             else:
+                                self._flush()
                                 self.sock_out.send_pyobj(GetImages())
+                    if not self.transfer.is_running:
+                        self._flush()
                     continue
+                self._flush()
                 msg = self.sock_in.recv_pyobj()
                 if self.process_message(msg):
                     break
         except KeyboardInterrupt:
             pass
         finally:
-            self.sock_out.send_pyobj(Shutdown())
+            try:
+                self._flush()
+            finally:
+                self.sock_out.send_pyobj(Shutdown())
+
+    _pending = None
+
+    def _flush(self):
+        """Send the iterate that is still in flight, if any (worker.py:351-353)."""
+        handle, self._pending = self._pending, None
+        if handle is not None:
+            image, trace = handle.result()
+            self.sock_out.send_pyobj(Iterate(np.array(image), handle.t, dict(trace)))
 
     def process_message(self, msg):
         """worker.py:366-409.  Returns True when the loop should end."""
