@@ -368,6 +368,210 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// ================================================================================================
+// Weight-stationary, halo-reuse variant for the full-resolution layers (cin <= 128, narrow N).
+//
+// With N = 64 one 64-wide K block is only 128 MMA cycles, but the generic kernel fetches a fresh
+// 16 KB A tile per tap for it: 9 x 16 KB per 128 pixels per channel block, more than the L2 -> shared
+// memory path delivers (ncu: conv1_2 at 28 % tensor pipe).  Here
+//   * the CTA's weights (all 9 taps x KB channel blocks of its N block) are loaded ONCE and stay in
+//     shared memory for the whole persistent kernel;
+//   * per 16 x 8 pixel tile and channel block ONE TMA box {64 ch, 16 px, 18 rows} = 36 KB (the tile plus
+//     its halo, rows 16 px = 2 KB apart) lands in shared memory, and the nine taps are nine UMMA
+//     descriptors into that patch: start = patch + (r*16 + s) * 128 B, stride between 8-pixel row groups
+//     (SBO) = 2048 B (base_offset stays 0: the swizzle follows absolute address bits, see smem_desc_patch).
+// A traffic drops 4x (36 KB instead of 144 KB); the layer becomes MMA / HBM bound.
+constexpr int kPatchW = 16, kPatchH = 18;
+constexpr int kPatchBytes = kPatchW * kPatchH * 128;          // 36 864 = 36 x 1024
+constexpr int kWsTW = 8, kWsTH = 16;
+
+template <int BN, int KB> struct WsCfg {
+  static constexpr int kWTile = BN * 128;                      // one tap, one channel block
+  static constexpr int kWBytes = KB * 9 * kWTile;
+  static constexpr int kStages = (kWBytes <= 73728) ? 4 : 2;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kWBytes + kStages * kPatchBytes + 1024 + 256;
+};
+
+// Start addresses are 128 B (one pixel) granular, not 1024 B aligned.  Measured on B200: the swizzle XOR
+// is taken from the absolute shared-memory address bits (the same bits the TMA unit used when it wrote
+// the patch), so the descriptor's base_offset field must stay 0 -- setting it to (addr >> 7) & 7 reads
+// the wrong 16-byte chunks for every tap with a column shift.
+__device__ __forceinline__ uint64_t smem_desc_patch(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(2048 >> 4) << 32;                            // SBO: next 8-pixel group = next patch row
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, int KB>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
+                  __half* __restrict__ out, const int epi, const TcInject inj) {
+  using C = WsCfg<BN, KB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_p = smem + C::kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kWBytes + C::kStages * kPatchBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
+  uint64_t* w_full = bars + 2 * C::kStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a CTA keeps one N block for its whole life (its weights are resident); pixel tiles are strided
+  const int nb = blockIdx.x % g.n_blocks;
+  const int pt0 = blockIdx.x / g.n_blocks, pt_step = gridDim.x / g.n_blocks;
+  const int n_pt = g.tiles_h * g.tiles_w;
+
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
+    tc::mbar_init(w_full, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, C::kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(w_full, C::kWBytes);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int tap = 0; tap < 9; ++tap)
+          tc::tma_load_2d(smem_w + (kb * 9 + tap) * C::kWTile, &tmap_b, w_full, tap * g.cin + kb * BK, nb * BN);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = pt0; pt < n_pt; pt += pt_step) {
+      const int th = pt / g.tiles_w, tw = pt - th * g.tiles_w;
+      const int h0 = th * kWsTH, w0 = tw * kWsTW;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (tc::elect_one()) {
+          if (g.dbg & 4) {
+            tc::mbar_arrive(&full_bar[stage]);
+          } else {
+            tc::mbar_expect_tx(&full_bar[stage], kPatchBytes);
+            tc::tma_load_3d(smem_p + stage * kPatchBytes, &tmap_a, &full_bar[stage], kb * BK, w0 - 1, h0 - 1 + g.hoff);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc = tc::idesc_f16(BM, BN, 0, 0);
+    const uint32_t p_addr0 = tc::smem_u32(smem_p);
+    const uint64_t b_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_w));
+    tc::mbar_wait(w_full, 0);
+    tc::fence_after_sync();
+    int stage = 0; uint32_t phase = 0;
+    int local = 0;
+    for (int pt = pt0; pt < n_pt; pt += pt_step, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t p_addr = p_addr0 + stage * kPatchBytes;
+#pragma unroll
+          for (int tap = 0; tap < ((g.dbg & 2) ? 0 : 9); ++tap) {
+            const uint64_t a_desc = smem_desc_patch(p_addr + ((tap / 3) * kPatchW + (tap % 3)) * 128);
+            const uint64_t b_desc = b_desc0 + (uint64_t)(((kb * 9 + tap) * C::kWTile) >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | tap | k) != 0);
+          }
+          tc::umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (tc::elect_one()) tc::umma_commit(&tmem_full[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ epilogue ====================================
+    const int ew = warp - kEpiWarp0;
+    const int row = ew * 32 + lane;
+    const int row_h = row / kWsTW, row_w = row % kWsTW;
+    float ss = 0.f;
+    float cc = 0.f, sc = 0.f, dc = 0.f;
+    if (inj.coef != nullptr) { cc = (float)inj.coef[0]; sc = (float)inj.coef[1]; dc = (float)inj.coef[2]; }
+    constexpr int NCH = BN / 32;
+    const bool masked = (epi == EPI_MASK);
+    const bool have_inj = masked && inj.coef != nullptr;
+    const bool have_s = have_inj && inj.sraw != nullptr;
+    int local = 0;
+    for (int pt = pt0; pt < n_pt; pt += pt_step, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int th = pt / g.tiles_w, tw = pt - th * g.tiles_w;
+      const int h = th * kWsTH + row_h, w = tw * kWsTW + row_w;
+      const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
+      const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      uint4 pa[NCH][4], ps[NCH][4];
+      if (valid && masked) {
+        const uint4* ap = reinterpret_cast<const uint4*>(act + obase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pa[c][q] = __ldg(ap + c * 4 + q);
+      }
+      if (valid && have_s) {
+        const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ps[c][q] = __ldg(sp + c * 4 + q);
+      }
+      if (lane == 0) tc::mbar_wait(&tmem_full[acc], acc_phase);
+      __syncwarp();
+      tc::fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(t_row + c * 32, r);
+        tc::tmem_ld_wait();
+        if (valid)
+          epi_chunk(r, epi, bias + nb * BN + c * 32, pa[c], ps[c],
+                    (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                    1.f, false, ss, out + obase + c * 32);
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -379,6 +583,7 @@ struct TcConvPlan {
   CUtensorMap tmap_a, tmap_b;
   ConvGeom g;
   int bn;
+  int ws_kb;        // > 0: weight-stationary halo-reuse kernel with this many 64-channel K blocks
 };
 
 static int get_encoder(st2_ctx* ctx, EncodeTiledFn* fn) {
@@ -440,6 +645,16 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
       if (cost < best * 0.97) { best = cost; p->bn = bn; }       // prefer the wider tile on near-ties
     }
   }
+  p->ws_kb = 0;
+  // Only where N = 64: there the generic kernel starves on A-tile fill.  (Measured: with N = 128 the two
+  // kernels tie -- conv2_1 fwd 54 vs 57 us, conv2_2 80 vs 78 us -- so those keep the generic path.)
+  if (taps == 9 && cin <= 128 && cout == 64 && W >= 16 && H >= 16 && !getenv("ST2_NO_WS")) {
+    p->ws_kb = cin / 64;
+    p->bn = 64;                                     // (64,1) (64,2): weights + 2..4 patches fit in 227 KB
+    g.TW = kWsTW; g.TH = kWsTH;
+    g.tiles_h = (H + g.TH - 1) / g.TH;
+    g.tiles_w = (W + g.TW - 1) / g.TW;
+  }
   g.n_blocks = cout / p->bn;
   g.total_tiles = g.tiles_h * g.tiles_w * g.n_blocks;
   g.cblocks = cin / BK;
@@ -448,6 +663,7 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)(H + 2 * halo)};
     cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH};
+    if (p->ws_kb) { box[1] = kPatchW; box[2] = kPatchH; }
     int rc = st2_encode_tmap(ctx, &p->tmap_a, in, 3, dims, strides, box);
     if (rc) { delete p; return rc; }
   }
@@ -484,6 +700,27 @@ static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   return 0;
 }
 
+template <int BN, int KB>
+static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
+                     const TcInject& inj) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_ws_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       WsCfg<BN, KB>::kSmemBytes));
+    attr_set = true;
+  }
+  const int nbk = p->g.n_blocks;
+  const int n_pt = p->g.tiles_h * p->g.tiles_w;
+  int per_nb = ctx->sm_count / nbk;
+  if (per_nb > n_pt) per_nb = n_pt;
+  if (per_nb < 1) per_nb = 1;
+  p->g.dbg = ctx->debug_flags;
+  tc_conv_ws_kernel<BN, KB><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
+      p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                    float out_scale, double* sumsq, const TcInject* inj_in) {
   if (epi == EPI_BIAS_RELU && !bias) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: bias required");
@@ -494,6 +731,12 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     if (epi != EPI_MASK) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: injection needs the mask epilogue");
     inj = *inj_in;
   }
+  if (p->ws_kb && out_scale == 1.f && sumsq == nullptr) {
+    if (p->ws_kb == 1 && p->bn == 64) return launch_ws<64, 1>(ctx, p, bias, act, out, epi, inj);
+    if (p->ws_kb == 1 && p->bn == 128) return launch_ws<128, 1>(ctx, p, bias, act, out, epi, inj);
+    if (p->ws_kb == 2 && p->bn == 64) return launch_ws<64, 2>(ctx, p, bias, act, out, epi, inj);
+    return st2_fail(ctx, ST2_ERR_STATE, "tc_conv: no weight-stationary kernel for this shape");
+  }
   switch (p->bn) {
     case 256: return launch_bn<256>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
     case 128: return launch_bn<128>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
@@ -501,4 +744,6 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
   }
 }
 
-static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>)});
+static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>),
+                                      ST2_KFN(tc_conv_ws_kernel<64, 1>), ST2_KFN(tc_conv_ws_kernel<128, 1>),
+                                      ST2_KFN(tc_conv_ws_kernel<64, 2>)});
