@@ -76,7 +76,10 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
                                           const uint4 (&a4)[4], const uint4 (&s4)[4], const __half* __restrict__ fc_c,
                                           const bool have_inj, const bool have_s, const float cc, const float sc,
                                           const float dc, const float out_scale, const bool want_ss, float& ss,
-                                          __half* __restrict__ out_c) {
+                                          __half* __restrict__ out_c, const int sw = 0) {
+  // out_c: where this chunk's four 16-byte pieces go.  sw = 0: consecutive (global memory).  sw != 0: out_c is
+  // a 128-byte row of a SWIZZLE_128B staging tile in shared memory, pieces q land at ((chunk0 + q) ^ row%8)
+  // with chunk0 = sw >> 3 and row%8 = sw & 7 (bit 6 set marks the mode).
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -146,7 +149,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
     __half2* hp = reinterpret_cast<__half2*>(&o);
 #pragma unroll
     for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-    op[q] = o;
+    if (sw == 0) op[q] = o;
+    else op[(((sw >> 3) & 7) + q) ^ (sw & 7)] = o;
   }
 }
 
@@ -388,9 +392,14 @@ constexpr int kWsTW = 8, kWsTH = 16;
 template <int BN, int KB> struct WsCfg {
   static constexpr int kWTile = BN * 128;                      // one tap, one channel block
   static constexpr int kWBytes = KB * 9 * kWTile;
-  static constexpr int kStages = (kWBytes <= 73728) ? 4 : 2;
+  // Output through shared memory + TMA tile stores where it fits (KB = 1): per-thread 16-byte stores at a
+  // 128-byte stride cap the epilogue at ~1.8 TB/s (measured 76 us for conv1_2's 134 MB with everything else
+  // switched off), whole-line bulk stores do not.
+  static constexpr bool kTmaStore = (KB == 1 && BN == 64);
+  static constexpr int kStages = kTmaStore ? 3 : 2;
+  static constexpr int kOutBytes = kTmaStore ? 2 * BM * 128 : 0;       // two 16 KB staging tiles
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kWBytes + kStages * kPatchBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kWBytes + kStages * kPatchBytes + kOutBytes + 1024 + 256;
 };
 
 // Start addresses are 128 B (one pixel) granular, not 1024 B aligned.  Measured on B200: the swizzle XOR
@@ -410,14 +419,15 @@ __device__ __forceinline__ uint64_t smem_desc_patch(uint32_t addr) {
 template <int BN, int KB>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
-                  __half* __restrict__ out, const int epi, const TcInject inj) {
+                  const __grid_constant__ CUtensorMap tmap_o, const ConvGeom g, const float* __restrict__ bias,
+                  const __half* __restrict__ act, __half* __restrict__ out, const int epi, const TcInject inj) {
   using C = WsCfg<BN, KB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;
   uint8_t* smem_p = smem + C::kWBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kWBytes + C::kStages * kPatchBytes);
+  uint8_t* smem_o = smem + C::kWBytes + C::kStages * kPatchBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kWBytes + C::kStages * kPatchBytes + C::kOutBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
@@ -431,7 +441,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int pt0 = blockIdx.x / g.n_blocks, pt_step = gridDim.x / g.n_blocks;
   const int n_pt = g.tiles_h * g.tiles_w;
 
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); tc::prefetch_tmap(&tmap_o); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
@@ -530,24 +540,101 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
       uint4 pa[NCH][4], ps[NCH][4];
-      if (valid && masked) {
-        const uint4* ap = reinterpret_cast<const uint4*>(act + obase);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) pa[c][q] = __ldg(ap + c * 4 + q);
+      if (masked) {
+        // pull the NEXT tile's epilogue operands towards L2 now: per tile the loads below are issued and then
+        // immediately needed, so their latency (not their bandwidth) is what the epilogue pays
+        const int ptn = pt + pt_step;
+        if (ptn < n_pt) {
+          const int thn = ptn / g.tiles_w, twn = ptn - thn * g.tiles_w;
+          const int hn = thn * kWsTH + row_h, wn = twn * kWsTW + row_w;
+          if (hn < g.H && wn < g.W) {
+            const long long on = ((long long)hn * g.W + wn) * g.cout + (long long)nb * BN;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(act + on));
+            if (have_s) asm volatile("prefetch.global.L2 [%0];" ::"l"(inj.sraw + on));
+          }
+        }
       }
-      if (valid && have_s) {
-        const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase);
+      if (C::kTmaStore) {
+        // Coalesced fetch: the warp's 32 pixels are 4 tile rows of 8 pixels = 4 x 1 KB contiguous in global
+        // memory (cout = 64).  Load j takes 512 contiguous bytes; the pieces are re-sorted to "thread = pixel"
+        // through the warp's own 4 KB slice of the staging tile further down.
+        if (masked) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
+          for (int j = 0; j < 8; ++j) {
+            const int hh = th * kWsTH + ew * 4 + (j >> 1), ww = tw * kWsTW + (j & 1) * 4 + (lane >> 3);
+            const long long o = ((long long)hh * g.W + ww) * g.cout + (lane & 7) * 8;
+            const bool ok = hh < g.H && ww < g.W && !(g.dbg & 1);
+            pa[j >> 2][j & 3] = ok ? __ldg(reinterpret_cast<const uint4*>(act + o)) : make_uint4(0, 0, 0, 0);
+            if (have_s) ps[j >> 2][j & 3] = ok ? __ldg(reinterpret_cast<const uint4*>(inj.sraw + o)) : make_uint4(0, 0, 0, 0);
+          }
+        }
+      } else {
+        if (valid && masked) {
+          const uint4* ap = reinterpret_cast<const uint4*>(act + obase);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) ps[c][q] = __ldg(sp + c * 4 + q);
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pa[c][q] = __ldg(ap + c * 4 + q);
+        }
+        if (valid && have_s) {
+          const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ps[c][q] = __ldg(sp + c * 4 + q);
+        }
       }
       if (lane == 0) tc::mbar_wait(&tmem_full[acc], acc_phase);
       __syncwarp();
       tc::fence_after_sync();
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+      if (C::kTmaStore) {
+        // staging tile `acc`: the bulk store issued from it two tiles ago must have finished reading it
+        uint8_t* stg = smem_o + acc * (BM * 128);
+        if (warp == kEpiWarp0 && lane == 0) tc::bulk_wait_read<1>();
+        tc::named_bar_sync(1, 128);
+        __half* srow = reinterpret_cast<__half*>(stg + row * 128);
+        if (masked) {
+          // re-sort the coalesced pieces: piece j of lane l belongs to staging row (ew*4 + j/2)*8 + (j%2)*4 + l/8,
+          // chunk l%8; afterwards every thread reads the eight chunks of its own row
+          uint4* sl = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && !have_s) break;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rr = (ew * 4 + (j >> 1)) * 8 + (j & 1) * 4 + (lane >> 3);
+              sl[rr * 8 + ((lane & 7) ^ (rr & 7))] = pass ? ps[j >> 2][j & 3] : pa[j >> 2][j & 3];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 t = sl[row * 8 + (j ^ (row & 7))];
+              if (pass) ps[j >> 2][j & 3] = t; else pa[j >> 2][j & 3] = t;
+            }
+            __syncwarp();
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(t_row + c * 32, r);
+          tc::tmem_ld_wait();
+          epi_chunk(r, epi, bias + nb * BN + c * 32, pa[c], ps[c],
+                    (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc,
+                    dc, 1.f, false, ss, srow, 64 | ((c * 4) << 3) | (row & 7));
+        }
+        tc::fence_before_sync();
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+        tc::named_bar_sync(1, 128);
+        if (warp == kEpiWarp0 && lane == 0 && !(g.dbg & 1)) {
+          tc::tma_store_3d(&tmap_o, stg, nb * BN, tw * kWsTW, th * kWsTH);
+          tc::bulk_commit();
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         uint32_t r[32];
@@ -562,6 +649,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
     }
+    if (C::kTmaStore && warp == kEpiWarp0 && lane == 0) tc::bulk_wait<0>();
   }
 
   tc::fence_before_sync();
@@ -584,6 +672,8 @@ struct TcConvPlan {
   ConvGeom g;
   int bn;
   int ws_kb;        // > 0: weight-stationary halo-reuse kernel with this many 64-channel K blocks
+  CUtensorMap tmap_o;           // output tile stores of the weight-stationary kernel, encoded on first use
+  const void* tmap_o_base = nullptr;
 };
 
 static int get_encoder(st2_ctx* ctx, EncodeTiledFn* fn) {
@@ -709,6 +799,14 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
                                        WsCfg<BN, KB>::kSmemBytes));
     attr_set = true;
   }
+  if (p->tmap_o_base != (const void*)out) {
+    cuuint64_t dims[3] = {(cuuint64_t)p->g.cout, (cuuint64_t)p->g.W, (cuuint64_t)p->g.H};
+    cuuint64_t strides[2] = {(cuuint64_t)p->g.cout * 2, (cuuint64_t)p->g.W * p->g.cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BN, (cuuint32_t)kWsTW, (cuuint32_t)kWsTH};
+    int rc = st2_encode_tmap(ctx, &p->tmap_o, out, 3, dims, strides, box);
+    if (rc) return rc;
+    p->tmap_o_base = out;
+  }
   const int nbk = p->g.n_blocks;
   const int n_pt = p->g.tiles_h * p->g.tiles_w;
   int per_nb = ctx->sm_count / nbk;
@@ -716,7 +814,7 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   if (per_nb < 1) per_nb = 1;
   p->g.dbg = ctx->debug_flags;
   tc_conv_ws_kernel<BN, KB><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
-      p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
+      p->tmap_a, p->tmap_b, p->tmap_o, p->g, bias, act, out, epi, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
