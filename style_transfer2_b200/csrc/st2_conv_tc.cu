@@ -396,9 +396,10 @@ template <int BN, int KB> struct WsCfg {
   // 128-byte stride cap the epilogue at ~1.8 TB/s (measured 76 us for conv1_2's 134 MB with everything else
   // switched off), whole-line bulk stores do not.
   static constexpr bool kTmaStore = (KB == 1 && BN == 64);
-  static constexpr int kStages = kTmaStore ? 3 : 2;
+  static constexpr int kStages = kTmaStore ? 3 : (kWBytes <= 73728 ? 4 : 2);
   static constexpr int kOutBytes = kTmaStore ? 2 * BM * 128 : 0;       // two 16 KB staging tiles
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kAccStride = BN < 32 ? 32 : BN;                 // TMEM columns per accumulator
+  static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kSmemBytes = kWBytes + kStages * kPatchBytes + kOutBytes + 1024 + 256;
 };
 
@@ -496,7 +497,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t acc_phase = (local >> 1) & 1;
       tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc::fence_after_sync();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * C::kAccStride;
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
         tc::mbar_wait(&full_bar[stage], phase);
@@ -527,7 +528,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float ss = 0.f;
     float cc = 0.f, sc = 0.f, dc = 0.f;
     if (inj.coef != nullptr) { cc = (float)inj.coef[0]; sc = (float)inj.coef[1]; dc = (float)inj.coef[2]; }
-    constexpr int NCH = BN / 32;
+    constexpr int NCH = BN >= 32 ? BN / 32 : 1;
     const bool masked = (epi == EPI_MASK);
     const bool have_inj = masked && inj.coef != nullptr;
     const bool have_s = have_inj && inj.sraw != nullptr;
@@ -539,6 +540,26 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int h = th * kWsTH + row_h, w = tw * kWsTW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      if (BN == 16) {
+        // conv1_1 data gradient: 64 gradient channels -> the 3 image planes (N padded to 16), fp32 NCHW out
+        if (lane == 0) tc::mbar_wait(&tmem_full[acc], acc_phase);
+        __syncwarp();
+        tc::fence_after_sync();
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + acc * C::kAccStride + ((uint32_t)(ew * 32) << 16), r);
+        tc::tmem_ld_wait();
+        if (valid) {
+          float* gx = reinterpret_cast<float*>(out);
+          const long long plane = (long long)g.H * g.W, p = (long long)h * g.W + w;
+          gx[p] = __uint_as_float(r[0]);
+          gx[plane + p] = __uint_as_float(r[1]);
+          gx[2 * plane + p] = __uint_as_float(r[2]);
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
       uint4 pa[NCH][4], ps[NCH][4];
       if (masked) {
         // pull the NEXT tile's epilogue operands towards L2 now: per tile the loads below are issued and then
@@ -587,7 +608,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (lane == 0) tc::mbar_wait(&tmem_full[acc], acc_phase);
       __syncwarp();
       tc::fence_after_sync();
-      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+      const uint32_t t_row = tmem_base + acc * C::kAccStride + ((uint32_t)(ew * 32) << 16);
       if (C::kTmaStore) {
         // staging tile `acc`: the bulk store issued from it two tiles ago must have finished reading it
         uint8_t* stg = smem_o + acc * (BM * 128);
@@ -704,7 +725,9 @@ int st2_encode_tmap(st2_ctx* ctx, CUtensorMap* map, const void* base, int rank, 
 
 int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, int H, int W, int cin, int cout,
                         int taps, TcConvPlan** out, int halo) {
-  if (cin % 64 || cout % 64 || (taps != 9 && taps != 1))
+  const bool first_bwd = (cin == 64 && cout == 16 && taps == 9);     // conv1_1 data gradient, 3 planes padded to 16
+  if (first_bwd && (W < 16 || H < 16)) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: canvas too small for the conv1_1 gradient kernel");
+  if (!first_bwd && (cin % 64 || cout % 64 || (taps != 9 && taps != 1)))
     return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: cin/cout must be multiples of 64 (got %d/%d)", cin, cout);
   TcConvPlan* p = new TcConvPlan();
   ConvGeom& g = p->g;
@@ -724,7 +747,7 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
     const char* force = getenv("ST2_TC_BN");
     for (int c = 0; c < 3; ++c) {
       const int bn = cand[c];
-      if (cout % bn) continue;
+      if (cout % bn || first_bwd) continue;
       if (force && atoi(force) == bn) { p->bn = bn; best = -1; break; }
       const long long tiles = (long long)g.tiles_h * g.tiles_w * (cout / bn);
       const long long waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
@@ -738,9 +761,9 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   p->ws_kb = 0;
   // Only where N = 64: there the generic kernel starves on A-tile fill.  (Measured: with N = 128 the two
   // kernels tie -- conv2_1 fwd 54 vs 57 us, conv2_2 80 vs 78 us -- so those keep the generic path.)
-  if (taps == 9 && cin <= 128 && cout == 64 && W >= 16 && H >= 16 && !getenv("ST2_NO_WS")) {
+  if (first_bwd || (taps == 9 && cin <= 128 && cout == 64 && W >= 16 && H >= 16 && !getenv("ST2_NO_WS"))) {
     p->ws_kb = cin / 64;
-    p->bn = 64;                                     // (64,1) (64,2): weights + 2..4 patches fit in 227 KB
+    p->bn = first_bwd ? 16 : 64;                    // (64,1) (64,2) (16,1): weights + 2..4 patches fit in 227 KB
     g.TW = kWsTW; g.TH = kWsTH;
     g.tiles_h = (H + g.TH - 1) / g.TH;
     g.tiles_w = (W + g.TW - 1) / g.TW;
@@ -799,7 +822,7 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
                                        WsCfg<BN, KB>::kSmemBytes));
     attr_set = true;
   }
-  if (p->tmap_o_base != (const void*)out) {
+  if (WsCfg<BN, KB>::kTmaStore && p->tmap_o_base != (const void*)out) {
     cuuint64_t dims[3] = {(cuuint64_t)p->g.cout, (cuuint64_t)p->g.W, (cuuint64_t)p->g.H};
     cuuint64_t strides[2] = {(cuuint64_t)p->g.cout * 2, (cuuint64_t)p->g.W * p->g.cout * 2};
     cuuint32_t box[3] = {(cuuint32_t)BN, (cuuint32_t)kWsTW, (cuuint32_t)kWsTH};
@@ -819,6 +842,13 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   return 0;
 }
 
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx) {
+  if (!p || p->bn != 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
+  TcInject inj;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr;
+  return launch_ws<16, 1>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
+}
+
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                    float out_scale, double* sumsq, const TcInject* inj_in) {
   if (epi == EPI_BIAS_RELU && !bias) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: bias required");
@@ -833,6 +863,7 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     if (p->ws_kb == 1 && p->bn == 64) return launch_ws<64, 1>(ctx, p, bias, act, out, epi, inj);
     if (p->ws_kb == 1 && p->bn == 128) return launch_ws<128, 1>(ctx, p, bias, act, out, epi, inj);
     if (p->ws_kb == 2 && p->bn == 64) return launch_ws<64, 2>(ctx, p, bias, act, out, epi, inj);
+    if (p->ws_kb == 1 && p->bn == 16) return launch_ws<16, 1>(ctx, p, bias, act, out, EPI_RAW, inj);
     return st2_fail(ctx, ST2_ERR_STATE, "tc_conv: no weight-stationary kernel for this shape");
   }
   switch (p->bn) {
@@ -844,4 +875,4 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
 
 static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>),
                                       ST2_KFN(tc_conv_ws_kernel<64, 1>), ST2_KFN(tc_conv_ws_kernel<128, 1>),
-                                      ST2_KFN(tc_conv_ws_kernel<64, 2>)});
+                                      ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>)});

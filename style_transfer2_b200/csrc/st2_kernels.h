@@ -82,6 +82,9 @@ void tc_conv_plan_destroy(TcConvPlan* p);
 struct TcInject { const __half* fc; const __half* sraw; const double* coef; };
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                    float out_scale, double* sumsq, const TcInject* inj = nullptr);
+// conv1_1 data gradient on the tensor cores: plan made with cin = 64, cout = 16 (the 3 image planes padded),
+// weights [16][tap'][64] fp16; writes fp32 NCHW (3 dense planes of H x W)
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx);
 // Gram partials with tcgen05 (MN-major operands): Gd += F^T F for fp16 NHWC features
 struct TcGramPlan;
 int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGramPlan** out);

@@ -76,7 +76,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
     f_fwd[((long long)tap * cin + ci) * cout + co] = v;              // [tap][ci][co]
     f_bwd[((long long)tapf * cout + co) * cin + ci] = v;             // [tap'][co][ci]
     if (h_fwd) h_fwd[((long long)co * 9 + tap) * cin + ci] = __float2half_rn(v);     // [co][tap][ci]
-    if (h_bwd) h_bwd[((long long)ci * 9 + tapf) * cout + co] = __float2half_rn(v);   // [ci][tap'][co]
+    if (h_bwd) h_bwd[((long long)ci * 9 + tapf) * cout + co] = __float2half_rn(v);   // [ci][tap'][co] (conv1_1: 16 rows, 3 used)
   }
 }
 
@@ -507,7 +507,9 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
     ProfScope ps(ctx, bcat);
     if (is_conv) {
       const int ci = g_blobs[i].conv_index;
-      if (ci == 0) {
+      if (ci == 0 && cur.tc_bwd) {
+        rc = tc_conv_first_bwd_launch(ctx, cur.tc_bwd, grad_out);
+      } else if (ci == 0) {
         rc = launch_conv_first_bwd<T>(ctx, (const T*)cur.grad, ctx->wf32_bwd[0], grad_out, cur.H, cur.W, lo, hi);
       } else if (pl->prec == ST2_PREC_FP32) {
         rc = launch_conv_exact(ctx, (const float*)cur.grad, ctx->wf32_bwd[ci], nullptr, (const float*)below.act,
@@ -860,6 +862,10 @@ int st2_set_conv_weights(st2_ctx* ctx, int ci, const float* w, const float* b, i
   if (ci > 0) {
     if ((rc = ensure(ctx, (void**)&ctx->wh_fwd[ci], nw * 2))) return rc;
     if ((rc = ensure(ctx, (void**)&ctx->wh_bwd[ci], nw * 2))) return rc;
+  } else {
+    // conv1_1 data gradient on the tensor cores: N = 3 image planes padded to 16 rows of zeros
+    if ((rc = ensure(ctx, (void**)&ctx->wh_bwd[0], (size_t)16 * 9 * cout * 2))) return rc;
+    ST2_CUDA(ctx, cudaMemsetAsync(ctx->wh_bwd[0], 0, (size_t)16 * 9 * cout * 2, ctx->stream));
   }
   ctx->cin[ci] = cin; ctx->cout[ci] = cout;
   ST2_CUDA(ctx, cudaMemcpyAsync(ctx->w_oihw[ci], w, nw * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -913,6 +919,12 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
   ST2_CUDA(ctx, cudaMalloc(&pl->bwd, sizeof(float) * pl->b[0].n()));
   if (prec == ST2_PREC_FP16) {
     const int halo = strip ? 1 : 0;
+    if (ctx->wh_bwd[0] && pl->b[1].H >= 16 && pl->b[1].W >= 16 && !getenv("ST2_NO_TC_FIRST")) {
+      Blob& c11 = pl->b[1];
+      int rc = tc_conv_plan_create(ctx, (const __half*)(strip ? c11.grad_pad : c11.grad), ctx->wh_bwd[0], c11.H, c11.W, 64, 16,
+                                   9, &c11.tc_bwd, halo);
+      if (rc) return rc;
+    }
     for (int i = 2; i < ST2_NUM_BLOBS; ++i) {
       if (g_blobs[i].kind != KIND_CONV) continue;
       const int ci = g_blobs[i].conv_index;
