@@ -50,6 +50,7 @@ struct st2_ctx {
   // tensor-core packs (fp16, K-major): forward [co][tap][ci], backward [ci][tap'][co]
   __half* wh_fwd[ST2_NUM_CONVS] = {};
   __half* wh_bwd[ST2_NUM_CONVS] = {};
+  __half* wh_first = nullptr;      // conv1_1 forward pack for the sliding-window tensor-core kernel
   void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled entry point
   long long launches = 0;          // kernels launched through this context
   int debug_flags = 0;             // timing experiments only (st2_debug_flags)

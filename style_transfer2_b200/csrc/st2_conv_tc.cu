@@ -723,6 +723,21 @@ int st2_encode_tmap(st2_ctx* ctx, CUtensorMap* map, const void* base, int rank, 
   return 0;
 }
 
+// same with a choice of shared-memory layout: swizzle128 = 0 -> no swizzle (dense boxes)
+int st2_encode_tmap_ex(st2_ctx* ctx, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle128) {
+  EncodeTiledFn enc;
+  int rc = get_encoder(ctx, &enc);
+  if (rc) return rc;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return st2_fail(ctx, ST2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, int H, int W, int cin, int cout,
                         int taps, TcConvPlan** out, int halo) {
   const bool first_bwd = (cin == 64 && cout == 16 && taps == 9);     // conv1_1 data gradient, 3 planes padded to 16

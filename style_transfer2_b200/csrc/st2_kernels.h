@@ -85,6 +85,14 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
 // conv1_1 data gradient on the tensor cores: plan made with cin = 64, cout = 16 (the 3 image planes padded),
 // weights [16][tap'][64] fp16; writes fp32 NCHW (3 dense planes of H x W)
 int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx);
+// ---- st2_conv_first_tc.cu: conv1_1 forward on the tensor cores (sliding-window K over pixel pairs) ---------
+struct TcFirstPlan;
+int tc_first_plan_create(st2_ctx* ctx, int H, int W, int halo_strip, TcFirstPlan** out);
+void tc_first_plan_destroy(TcFirstPlan* p);
+int tc_first_pack_weights(st2_ctx* ctx, const float* w_oihw, __half* out /* 2 x 6144 halves: hi and lo parts */);
+// x: row 0 of plane 0 of the H rows (planes xps floats apart, 0 = dense); lo / hi: halo rows addressable
+int tc_first_fwd_launch(st2_ctx* ctx, TcFirstPlan* p, const float* x, long long xps, int lo, int hi, const __half* wpk,
+                        const float* bias, __half* out);
 // Gram partials with tcgen05 (MN-major operands): Gd += F^T F for fp16 NHWC features
 struct TcGramPlan;
 int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGramPlan** out);

