@@ -257,35 +257,50 @@ __global__ void lbfgs_take_g(LbfgsDev* st_) {
 
 // ---- two-loop recursion on coefficients (optimizers.py:89-108) ------------------------------------
 __global__ void lbfgs_coefficients(LbfgsDev* st_, double n_total) {
-  if (threadIdx.x != 0) return;
-  const int m = st_->count, head = st_->head;
-  int ph[MAXM];
-  double a[MAXM], b[MAXM], alpha[MAXM];
-  for (int j = 0; j < MAXM; ++j) { ph[j] = (head + j) % SLOTS; a[j] = 0.0; b[j] = 0.0; alpha[j] = 0.0; }
-  double cg = 1.0;
-  for (int i = m - 1; i >= 0; --i) {                      // newest -> oldest; q has g and Y components only
-    double sq = cg * st_->gS[ph[i]];
-    for (int j = 0; j < m; ++j) sq += b[j] * st_->SY[ph[i]][ph[j]];
-    alpha[i] = sq / st_->sy[ph[i]];
-    b[i] -= alpha[i];
+  // the tables come to shared memory in one coalesced sweep; the recursion itself is ~4 m^2 dependent double
+  // operations on one thread (global-memory latency per operand made this kernel 14 us, now ~3)
+  __shared__ LbfgsDev sh;
+  static_assert(sizeof(LbfgsDev) % 8 == 0, "LbfgsDev is copied as doubles");
+  {
+    const double* src = reinterpret_cast<const double*>(st_);
+    double* dst = reinterpret_cast<double*>(&sh);
+    for (int i = threadIdx.x; i < (int)(sizeof(LbfgsDev) / 8); i += blockDim.x) dst[i] = src[i];
   }
-  if (m > 0) {
-    const double gamma = (double)(float)(st_->sy[ph[m - 1]] / st_->yy[ph[m - 1]]);
-    cg *= gamma;
-    for (int j = 0; j < m; ++j) b[j] *= gamma;
-  } else {
-    cg = 1.0 / sqrt(st_->gg / n_total);                   // unit-RMS first step
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int m = sh.count, head = sh.head;
+    int ph[MAXM];
+    double a[MAXM], b[MAXM], alpha[MAXM];
+    for (int j = 0; j < MAXM; ++j) { ph[j] = (head + j) % SLOTS; a[j] = 0.0; b[j] = 0.0; alpha[j] = 0.0; }
+    double cg = 1.0;
+    for (int i = m - 1; i >= 0; --i) {                    // newest -> oldest; q has g and Y components only
+      double sq = cg * sh.gS[ph[i]];
+      for (int j = 0; j < m; ++j) sq += b[j] * sh.SY[ph[i]][ph[j]];
+      alpha[i] = sq / sh.sy[ph[i]];
+      b[i] -= alpha[i];
+    }
+    if (m > 0) {
+      const double gamma = (double)(float)(sh.sy[ph[m - 1]] / sh.yy[ph[m - 1]]);
+      cg *= gamma;
+      for (int j = 0; j < m; ++j) b[j] *= gamma;
+    } else {
+      cg = 1.0 / sqrt(sh.gg / n_total);                   // unit-RMS first step
+    }
+    for (int i = 0; i < m; ++i) {                         // oldest -> newest
+      double yq = cg * sh.gY[ph[i]];
+      for (int j = 0; j < m; ++j) yq += b[j] * sh.YY[ph[i]][ph[j]] + a[j] * sh.SY[ph[j]][ph[i]];
+      const double beta = yq / sh.sy[ph[i]];
+      a[i] += alpha[i] - beta;
+    }
+    sh.cg = cg;
+    for (int j = 0; j < SLOTS; ++j) { sh.a[j] = 0.0; sh.b[j] = 0.0; }
+    for (int j = 0; j < m; ++j) { sh.a[ph[j]] = a[j]; sh.b[ph[j]] = b[j]; }
   }
-  for (int i = 0; i < m; ++i) {                           // oldest -> newest
-    double yq = cg * st_->gY[ph[i]];
-    for (int j = 0; j < m; ++j) yq += b[j] * st_->YY[ph[i]][ph[j]] + a[j] * st_->SY[ph[j]][ph[i]];
-    const double beta = yq / st_->sy[ph[i]];
-    a[i] += alpha[i] - beta;
-  }
-  st_->cg = cg;
-  for (int j = 0; j < SLOTS; ++j) { st_->a[j] = 0.0; st_->b[j] = 0.0; }
-  for (int j = 0; j < m; ++j) { st_->a[ph[j]] = a[j]; st_->b[ph[j]] = b[j]; }
-  for (int i = 0; i < SUM_TOTAL; ++i) st_->sums[i] = 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) st_->cg = sh.cg;
+  for (int j = threadIdx.x; j < SLOTS; j += blockDim.x) { st_->a[j] = sh.a[j]; st_->b[j] = sh.b[j]; }
+  // every sum is consumed by now: zero the block for pass B (s_new . Y_j) and the next pass A
+  for (int i = threadIdx.x; i < SUM_TOTAL; i += blockDim.x) st_->sums[i] = 0.0;
 }
 
 // ---- pass B: s = -step * direction -> S[new]; x += s; s.Y_j ---------------------------------------
@@ -355,6 +370,7 @@ struct st2_lbfgs {
   double n_total;       // global length (== n on one GPU; sum over ranks when row-tiled)
   int n_corr;
   bool have_gdots;      // gS/gY/gg describe the gradient that the next advance will use
+  bool sums_clean;      // sums[0, SUM_SNY) known to be zero (set by advance_end)
   float *S, *Y;
   LbfgsDev* st;
 };
@@ -372,7 +388,7 @@ int st2_lbfgs_create(st2_ctx* ctx, long long n, int n_corr, st2_lbfgs** out) {
   if (!ctx || !out || n <= 0 || n_corr < 1 || n_corr > MAXM)
     return st2_fail(ctx, ST2_ERR_ARG, "st2_lbfgs_create: bad arguments (n=%lld n_corr=%d)", n, n_corr);
   st2_lbfgs* o = new st2_lbfgs();
-  o->ctx = ctx; o->n = n; o->n_total = (double)n; o->n_corr = n_corr; o->have_gdots = false;
+  o->ctx = ctx; o->n = n; o->n_total = (double)n; o->n_corr = n_corr; o->have_gdots = false; o->sums_clean = false;
   ST2_CUDA(ctx, cudaMalloc(&o->S, sizeof(float) * n * SLOTS));
   ST2_CUDA(ctx, cudaMalloc(&o->Y, sizeof(float) * n * SLOTS));
   ST2_CUDA(ctx, cudaMalloc(&o->st, sizeof(LbfgsDev)));
@@ -394,6 +410,7 @@ int st2_lbfgs_reset(st2_lbfgs* o) {
   ST2_CUDA(o->ctx, cudaMemcpyAsync(o->st, &h, sizeof(h), cudaMemcpyHostToDevice, o->ctx->stream));
   ST2_CUDA(o->ctx, cudaStreamSynchronize(o->ctx->stream));     // h is on this stack frame
   o->have_gdots = false;
+  o->sums_clean = false;
   return 0;
 }
 
@@ -427,10 +444,11 @@ int st2_lbfgs_advance_end(st2_lbfgs* o, float* x, const float* g, float step) {
     lbfgs_take_g<<<1, 32, 0, s>>>(o->st);
     ST2_LAUNCH_CHECK(ctx);
   }
-  lbfgs_coefficients<<<1, 32, 0, s>>>(o->st, o->n_total);
+  lbfgs_coefficients<<<1, 128, 0, s>>>(o->st, o->n_total);
   ST2_LAUNCH_CHECK(ctx);
   LAUNCH_V(lbfgs_pass_b, grid_for(o->n, ctx->sm_count), o->st, o->S, o->Y, g, x, o->n, step);
   o->have_gdots = false;
+  o->sums_clean = true;
   return 0;
 }
 
@@ -445,8 +463,12 @@ int st2_lbfgs_commit_begin(st2_lbfgs* o, const float* g_new, const float* g_prev
   st2_ctx* ctx = o->ctx;
   cudaStream_t s = ctx->stream;
   ProfScope ps(ctx, 7);
-  lbfgs_clear_sums<<<1, 64, 0, s>>>(o->st, 0, SUM_SNY);   // keep s_new . Y_j of the step just taken
-  ST2_LAUNCH_CHECK(ctx);
+  // sums [0, SUM_SNY) are zero here: lbfgs_coefficients cleared the block and only pass B (s_new . Y_j) wrote since
+  if (!o->sums_clean) {
+    lbfgs_clear_sums<<<1, 64, 0, s>>>(o->st, 0, SUM_SNY);
+    ST2_LAUNCH_CHECK(ctx);
+  }
+  o->sums_clean = false;
   LAUNCH_V(lbfgs_pass_a, grid_for(o->n, ctx->sm_count), o->st, o->S, o->Y, g_new, g_prev, o->n);
   return 0;
 }
