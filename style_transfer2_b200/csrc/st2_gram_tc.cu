@@ -150,8 +150,17 @@ __global__ void gram_finalize_partials_kernel(const float* __restrict__ partials
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int k = 0; k < nsplit; ++k) s += (double)partials[(long long)k * n + i];
+    // four independent chains: the loop is latency-bound (up to 148 splits, one L2 round trip each)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= nsplit; k += 4) {
+      s0 += (double)partials[(long long)k * n + i];
+      s1 += (double)partials[(long long)(k + 1) * n + i];
+      s2 += (double)partials[(long long)(k + 2) * n + i];
+      s3 += (double)partials[(long long)(k + 3) * n + i];
+    }
+    for (; k < nsplit; ++k) s0 += (double)partials[(long long)k * n + i];
+    const double s = (s0 + s1) + (s2 + s3);
     float gv = (float)s / denom;
     if (A != nullptr) gv -= A[i];
     D[i] = gv;
@@ -167,9 +176,16 @@ __global__ void gram_reduce_partials_kernel(const float* __restrict__ partials, 
                                             float* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int k = 0; k < nsplit; ++k) s += (double)partials[(long long)k * n + i];
-    out[i] = (float)s;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= nsplit; k += 4) {
+      s0 += (double)partials[(long long)k * n + i];
+      s1 += (double)partials[(long long)(k + 1) * n + i];
+      s2 += (double)partials[(long long)(k + 2) * n + i];
+      s3 += (double)partials[(long long)(k + 3) * n + i];
+    }
+    for (; k < nsplit; ++k) s0 += (double)partials[(long long)k * n + i];
+    out[i] = (float)((s0 + s1) + (s2 + s3));
   }
 }
 
@@ -251,9 +267,9 @@ int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double
   int rc = launch_mma(ctx, p);
   if (rc) return rc;
   const long long n = (long long)p->g.C * p->g.C;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
-  gram_finalize_partials_kernel<<<blocks, 256, 0, ctx->stream>>>(p->partials, p->g.splits, A, D, p->g.C, p->g.HW,
+  int blocks = (int)((n + 127) / 128);
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  gram_finalize_partials_kernel<<<blocks, 128, 0, ctx->stream>>>(p->partials, p->g.splits, A, D, p->g.C, p->g.HW,
                                                                  sum_dsq);
   ST2_LAUNCH_CHECK(ctx);
   return 0;

@@ -176,3 +176,28 @@ def test_read_config_accepts_the_stock_ini(tmp_path):
     cfg = utils.read_config(None, [tmp_path])
     assert cfg['worker_socket'].endswith('23899') and cfg.getint('gpu') == -1
     assert cfg.get('precision', 'fp16') == 'fp16'          # new knobs are optional
+
+
+def test_job_messages_follow_the_app_sequence_and_pickle():
+    """serving.job_messages builds what app.py sends for a fresh job (app.py:244-262): SetImages with a seeded
+    random uint8 input + content + style and reset_state, SetWeights, optional SetOptimizer, StartIteration --
+    and every message survives the pickle round trip the ZeroMQ transport applies."""
+    import pickle
+    from style_transfer2_b200 import messages as m, serving
+    content = np.zeros((32, 48, 3), np.uint8)
+    style = np.ones((20, 30, 3), np.uint8)
+    weights = {'content': {'conv4_2': 0.08}, 'style': {'conv1_1': 1.0}, 'deepdream': {}}
+    params = {'tv': 5, 'tv_power': 2, 'p': 50, 'p_power': 6}
+    msgs = serving.job_messages((32, 48), content, style, weights, params, seed=3)
+    assert [type(x) for x in msgs] == [m.SetImages, m.SetWeights, m.StartIteration]
+    si = msgs[0]
+    assert si.reset_state and si.size == (32, 48) and si.input_image.shape == (32, 48, 3)
+    assert si.input_image.dtype == np.uint8
+    np.testing.assert_array_equal(si.input_image, np.uint8(np.random.RandomState(3).uniform(0, 255, (32, 48, 3))))
+    adam = serving.job_messages(16, content[:16, :16], style, weights, params, optimizer='adam')
+    assert [type(x) for x in adam] == [m.SetImages, m.SetWeights, m.SetOptimizer, m.StartIteration]
+    assert adam[2].optimizer == 'adam' and adam[2].step_size == 10
+    m.install_as_toplevel()                       # what the worker does before it opens its sockets
+    for msg in msgs + adam:
+        back = pickle.loads(pickle.dumps(msg))
+        assert type(back) is type(msg) and sorted(vars(back)) == sorted(vars(msg))
