@@ -373,6 +373,211 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ================================================================================================
+// CTA-pair variant (cta_group::2) for the wide layers: two SMs of a TPC run one M = 256 x BN tile.
+// Each CTA loads its own 128 pixels of A and HALF of the weight tile (BN / 2 rows); the MMA reads B from
+// both shared memories, so per SM the operand traffic from shared memory drops from (128 + BN) to
+// (128 + BN / 2) rows per K step -- the single-CTA kernel at N = 256 is at ~96 B/clk of the 128 B/clk shared
+// memory port.  The pair tile is 16 rows x 16 pixels; CTA rank r owns rows 8r .. 8r+7 of it.
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
+                __half* __restrict__ out, const int epi, const TcInject inj) {
+  constexpr int KB = (BN == 256) ? 1 : 2;                      // K blocks per stage
+  constexpr int kABlock = BM * BK * 2;                         // 16 KB
+  constexpr int kBBlock = (BN / 2) * BK * 2;                   // this CTA's half of the weight tile
+  constexpr int kABytes = KB * kABlock, kBBytes = KB * kBBlock;
+  constexpr int kStages = (BN == 256) ? 6 : 4;
+  constexpr int kTmemCols = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes));
+  uint64_t* full_bar = bars;                         // used on the leader: both CTAs' TMA bytes land here
+  uint64_t* empty_bar = bars + kStages;              // local copy in each CTA (multicast commit)
+  uint64_t* tmem_full = bars + 2 * kStages;          // local copy in each CTA (multicast commit)
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;     // used on the leader: 4 local + 4 remote epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 8); }
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc_2sm(tmem_slot, kTmemCols);
+  tc::fence_before_sync();
+  tc::cluster_sync_all();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair tiles: (n block fastest, then tile column, then pair-tile row), strided by the number of pairs
+  const int n_tiles = g.tiles_h * g.tiles_w * g.n_blocks;      // tiles_h counts 16-row pair tiles here
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      const int nb = tile % g.n_blocks;
+      const int pt = tile / g.n_blocks;
+      const int w0 = (pt % g.tiles_w) * g.TW, h0 = (pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH;
+      int tap = 0, cb = 0;
+      for (int it = 0; it < g.k_iters; it += KB) {
+        const int nkb = (g.k_iters - it < KB) ? g.k_iters - it : KB;
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0 && tc::elect_one())
+          tc::mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)nkb * (kABlock + kBBlock));
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+          if (j < nkb) {
+            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            if (tc::elect_one()) {
+              tc::tma_load_3d_2sm(smem_a + stage * kABytes + j * kABlock, &tmap_a, &full_bar[stage], cb * BK, w0 + dw,
+                                  h0 + dh + g.hoff);
+              tc::tma_load_2d_2sm(smem_b + stage * kBBytes + j * kBBlock, &tmap_b, &full_bar[stage],
+                                  tap * g.cin + cb * BK, nb * BN + (int)rank * (BN / 2));
+            }
+            if (++cb == g.cblocks) { cb = 0; ++tap; }
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (leader only) ================================
+    constexpr uint32_t idesc = tc::idesc_f16(2 * BM, BN, 0, 0);
+    const uint64_t a_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_a));
+    const uint64_t b_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_b));
+    int stage = 0; uint32_t phase = 0;
+    int local = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++local) {
+      const int acc = local & 1;
+      tc::mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int it = 0; it < g.k_iters; it += KB) {
+        const int nkb = (g.k_iters - it < KB) ? g.k_iters - it : KB;
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kABytes >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kBBytes >> 4));
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+            if (j < nkb) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                tc::umma_f16_2sm(d_tmem, a_desc + (uint64_t)(j * (kABlock >> 4) + 2 * k),
+                                 b_desc + (uint64_t)(j * (kBBlock >> 4) + 2 * k), idesc, (it | j | k) != 0);
+            }
+          }
+          tc::umma_commit_2sm(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (tc::elect_one()) tc::umma_commit_2sm(&tmem_full[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ epilogue (both CTAs, own 128 pixels) ====================
+    const int ew = warp - kEpiWarp0;
+    const int row = ew * 32 + lane;
+    const int row_h = row / g.TW, row_w = row % g.TW;
+    float ss = 0.f;
+    float cc = 0.f, sc = 0.f, dc = 0.f;
+    if (inj.coef != nullptr) { cc = (float)inj.coef[0]; sc = (float)inj.coef[1]; dc = (float)inj.coef[2]; }
+    constexpr int NCH = BN / 32;
+    const bool masked = (epi == EPI_MASK);
+    const bool have_inj = masked && inj.coef != nullptr;
+    const bool have_s = have_inj && inj.sraw != nullptr;
+    int local = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++local) {
+      const int acc = local & 1;
+      const int nb = tile % g.n_blocks;
+      const int pt = tile / g.n_blocks;
+      const int h = (pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH + row_h;
+      const int w = (pt % g.tiles_w) * g.TW + row_w;
+      const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
+      const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      // narrow tiles: epilogue operands fetched before the accumulator wait (see tc_conv_kernel)
+      constexpr bool PF = (BN <= 128);
+      uint4 pa[PF ? NCH : 1][4], ps[PF ? NCH : 1][4];
+      if (PF) {
+        if (valid && masked) {
+          const uint4* ap = reinterpret_cast<const uint4*>(act + obase);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pa[c][q] = __ldg(ap + c * 4 + q);
+        }
+        if (valid && have_s) {
+          const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ps[c][q] = __ldg(sp + c * 4 + q);
+        }
+      }
+      if (lane == 0) tc::mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+      __syncwarp();
+      tc::fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+      if (PF) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(t_row + c * 32, r);
+          tc::tmem_ld_wait();
+          if (valid)
+            epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
+                      (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                      1.f, false, ss, out + obase + c * 32);
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < (PF ? 0 : NCH); ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(t_row + c * 32, r);
+        tc::tmem_ld_wait();
+        if (valid) {
+          uint4 a4[4], s4[4];
+          if (masked) {
+            const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a4[q] = __ldg(ap + q);
+          }
+          if (have_s) {
+            const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s4[q] = __ldg(sp + q);
+          }
+          epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
+                    (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc, 1.f,
+                    false, ss, out + obase + c * 32);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+
+  tc::fence_before_sync();
+  tc::cluster_sync_all();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+// ================================================================================================
 // Weight-stationary, halo-reuse variant for the full-resolution layers (cin <= 128, narrow N).
 //
 // With N = 64 one 64-wide K block is only 128 MMA cycles, but the generic kernel fetches a fresh
@@ -693,6 +898,7 @@ struct TcConvPlan {
   ConvGeom g;
   int bn;
   int ws_kb;        // > 0: weight-stationary halo-reuse kernel with this many 64-channel K blocks
+  bool pair;        // CTA-pair kernel (cta_group::2): tiles_h counts 16-row pair tiles, tmap_b box is BN / 2 rows
   CUtensorMap tmap_o;           // output tile stores of the weight-stationary kernel, encoded on first use
   const void* tmap_o_base = nullptr;
 };
@@ -784,6 +990,17 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
     g.tiles_w = (W + g.TW - 1) / g.TW;
   }
   g.n_blocks = cout / p->bn;
+  // CTA pairs for the wide layers when there is at least one wave of 16 x 16 pixel pair tiles
+  p->pair = false;
+  // (measured: N = 128 with a short K loop -- conv2_1 forward, 9 K blocks -- is faster on the single-CTA kernel)
+  if (!p->ws_kb && taps == 9 && p->bn >= 128 && g.TW == 16 && (p->bn == 256 || taps * (cin / BK) >= 18) &&
+      !getenv("ST2_NO_PAIR")) {
+    const long long pair_tiles = (long long)((H + 15) / 16) * g.tiles_w * g.n_blocks;
+    if (pair_tiles >= ctx->sm_count / 2) {
+      p->pair = true;
+      g.tiles_h = (H + 15) / 16;
+    }
+  }
   g.total_tiles = g.tiles_h * g.tiles_w * g.n_blocks;
   g.cblocks = cin / BK;
   g.k_iters = taps * g.cblocks;
@@ -798,7 +1015,7 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   {
     cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout};
     cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p->bn};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(p->pair ? p->bn / 2 : p->bn)};
     int rc = st2_encode_tmap(ctx, &p->tmap_b, w_packed, 2, dims, strides, box);
     if (rc) { delete p; return rc; }
   }
@@ -857,6 +1074,25 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   return 0;
 }
 
+template <int BN>
+static int launch_pair(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
+                       const TcInject& inj) {
+  constexpr int KB = (BN == 256) ? 1 : 2;
+  constexpr int kStages = (BN == 256) ? 6 : 4;
+  constexpr int smem = kStages * KB * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int pairs = ctx->sm_count / 2;
+  if (pairs > p->g.total_tiles) pairs = p->g.total_tiles;
+  p->g.dbg = ctx->debug_flags;
+  tc_conv2_kernel<BN><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx) {
   if (!p || p->bn != 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
   TcInject inj;
@@ -881,6 +1117,8 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     if (p->ws_kb == 1 && p->bn == 16) return launch_ws<16, 1>(ctx, p, bias, act, out, EPI_RAW, inj);
     return st2_fail(ctx, ST2_ERR_STATE, "tc_conv: no weight-stationary kernel for this shape");
   }
+  if (p->pair && out_scale == 1.f && sumsq == nullptr)
+    return p->bn == 256 ? launch_pair<256>(ctx, p, bias, act, out, epi, inj) : launch_pair<128>(ctx, p, bias, act, out, epi, inj);
   switch (p->bn) {
     case 256: return launch_bn<256>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
     case 128: return launch_bn<128>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
@@ -890,4 +1128,5 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
 
 static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>),
                                       ST2_KFN(tc_conv_ws_kernel<64, 1>), ST2_KFN(tc_conv_ws_kernel<128, 1>),
-                                      ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>)});
+                                      ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>),
+                                      ST2_KFN(tc_conv2_kernel<256>), ST2_KFN(tc_conv2_kernel<128>)});
