@@ -989,6 +989,9 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
     g.tiles_h = (H + g.TH - 1) / g.TH;
     g.tiles_w = (W + g.TW - 1) / g.TW;
   }
+  // ST2_FORCE_PAIR lets small test canvases reach the CTA-pair kernel (normally chosen by size)
+  const bool force_pair = getenv("ST2_FORCE_PAIR") != nullptr;
+  if (force_pair && !p->ws_kb && taps == 9 && cout >= 128) p->bn = (cout % 256 == 0) ? 256 : 128;
   g.n_blocks = cout / p->bn;
   // CTA pairs for the wide layers when there is at least one wave of 16 x 16 pixel pair tiles
   p->pair = false;
@@ -996,7 +999,7 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   if (!p->ws_kb && taps == 9 && p->bn >= 128 && g.TW == 16 && (p->bn == 256 || taps * (cin / BK) >= 18) &&
       !getenv("ST2_NO_PAIR")) {
     const long long pair_tiles = (long long)((H + 15) / 16) * g.tiles_w * g.n_blocks;
-    if (pair_tiles >= ctx->sm_count / 2) {
+    if (pair_tiles >= ctx->sm_count / 2 || force_pair) {
       p->pair = true;
       g.tiles_h = (H + 15) / 16;
     }

@@ -94,6 +94,41 @@ def test_strips_reproduce_the_whole_canvas_objective(models, precision, world, h
     tt.close()
 
 
+def test_cta_pair_kernels_forced_on_small_canvases(monkeypatch):
+    """The CTA-pair (cta_group::2) convolution kernel is normally chosen only when a layer has at least one
+    wave of 16 x 16 pixel pair tiles, i.e. never at test sizes.  ST2_FORCE_PAIR routes every eligible layer of a
+    small canvas through it -- whole canvas and 2 row strips (tensor map with halo rows) -- and the results must
+    agree with the default kernels' (same operands; only the fp32 summation grouping differs)."""
+    from style_transfer2_b200.model import B200Model
+    from style_transfer2_b200 import utils
+    x0, content, style = images(96, 80)
+    m = B200Model(precision='fp16')
+    utils.set_default_engine(m.engine)
+    ref = whole(m, x0, content, style)
+    loss_ref, grad_ref = ref.opfunc(ref.input)
+    tr_ref = dict(ref.traces[-1].data)
+    grad_ref = grad_ref.cpu().numpy()
+    monkeypatch.setenv('ST2_FORCE_PAIR', '1')
+    m2 = B200Model(precision='fp16')                       # fresh plans: the knob is read at plan creation
+    utils.set_default_engine(m2.engine)
+    got = whole(m2, x0, content, style)
+    loss, grad = got.opfunc(got.input)
+    tr = got.traces[-1].data
+    for k, v in tr_ref.items():
+        if k != 'time':
+            assert np.isclose(tr[k], v, rtol=1e-3), (k, tr[k], v)
+    assert rel_err(grad.cpu().numpy(), grad_ref) < 2e-3
+    tt = tiled(m2, x0, content, style, 2)
+    loss_t, grads = tt.opfunc()
+    tt.check()
+    trt = tt.traces[-1].data
+    for k, v in tr_ref.items():
+        if k != 'time':
+            assert np.isclose(trt[k], v, rtol=1e-3), (k, trt[k], v)
+    assert rel_err(tt.gather(grads).cpu().numpy(), grad_ref) < 2e-3
+    tt.close()
+
+
 def test_strips_match_the_cpu_oracle(models):
     """Directly against the oracle (reference semantics), not only against our own whole-canvas plan."""
     from oracle.caffe_cpu import CaffeCPUModel
