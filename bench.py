@@ -77,7 +77,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -92,7 +92,11 @@ class ClockSampler:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        # samples inside the timed region; the sampler runs from before the warm-up, so if the region was
+        # shorter than a sampling period fall back to the samples taken under the same load just around it
+        rows = ([r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or
+                [r for t, r in self.rows if t0 - 0.25 <= t <= t1 + 0.25 and len(r) >= 7] or
+                [r for _, r in self.rows if len(r) >= 7])
         if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
         sm = [float(r[0]) for r in rows]
@@ -182,7 +186,7 @@ class TiledJob:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--size', type=int, default=0)
     ap.add_argument('--workload', default='jobs', choices=['jobs', 'canvas', 'serving'])
@@ -276,10 +280,10 @@ def main():
     eng = st.engine
     jobs = 1 if canvas else world                 # whole-job units per step
     # ---- device-resident arm: `value`
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         st.step(fetch=False)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = eng.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()

@@ -1,10 +1,12 @@
 #!/usr/bin/env python3
 """DRAM traffic of the tcgen05 conv launches of ONE iteration from an `ncu --set full` report.
-usage: python profiles/ncu_traffic.py gpurun_out/prof.ncu-rep > profiles/<round>_tcconv_traffic.json
+usage: python profiles/ncu_traffic.py gpurun_out/prof.ncu-rep [offset] > profiles/<round>_tcconv_traffic.json
 
-The capture must hold the 29 tc_conv_kernel launches of one L-BFGS iteration in order: 12 forward 3x3
-convolutions (conv1_2 .. conv5_1), 5 style-gradient 1x1 contractions, 12 data-gradient convolutions.
-bench.py reads the JSON to fill roofline.traffic (bytes per 3x3 launch, averaged over the 24)."""
+The capture must hold (at least) the 30 tensor-core convolution launches of one L-BFGS iteration, which come
+in a fixed cyclic order: 12 forward 3x3 convolutions (conv1_2 .. conv5_1), 5 style-gradient 1x1 contractions,
+12 data-gradient convolutions (conv5_1 .. conv1_2), the conv1_1 data gradient.  `offset` = position in that
+cycle of the first captured launch (0 when the capture starts on an iteration boundary).
+bench.py reads the JSON to fill roofline.traffic (bytes per 3x3 launch, averaged over the 24 of conv1_2..conv5_1)."""
 import csv
 import json
 import subprocess
@@ -33,13 +35,27 @@ ir, iw, it = col('dram__bytes_read.sum'), col('dram__bytes_write.sum'), col('gpu
 itp = col('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active') if 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active' in hdr else None
 launches = []
 for r in rows[2:]:
-    launches.append({'kernel': r[col('Kernel Name')].split('(')[0][-24:],
+    launches.append({'kernel': r[col('Kernel Name')].split('(')[0].split('::')[-1],
                      'dram_read': to_bytes(r[ir], units[ir]), 'dram_write': to_bytes(r[iw], units[iw]),
                      'us_under_ncu': to_us(r[it], units[it]),
                      'tensor_pipe_pct': float(r[itp]) if itp is not None and r[itp] else None})
-assert len(launches) == 29, 'expected 29 tc_conv launches of one iteration, got %d' % len(launches)
-conv = launches[:12] + launches[17:]
-style = launches[12:17]
+offset = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+assert len(launches) >= 30, 'expected the 30 tensor-core conv launches of one iteration, got %d' % len(launches)
+launches = launches[:30]
+NAMES = ['conv1_2', 'conv2_1', 'conv2_2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv3_4', 'conv4_1', 'conv4_2', 'conv4_3',
+         'conv4_4', 'conv5_1']
+conv, style, first = [], [], []
+for i, l in enumerate(launches):
+    pos = (i + offset) % 30
+    if pos < 12:
+        l['what'] = NAMES[pos] + ' fwd'; conv.append(l)
+    elif pos < 17:
+        l['what'] = 'style grad %d' % (pos - 12); style.append(l)
+    elif pos < 29:
+        l['what'] = NAMES[28 - pos] + ' dgrad'; conv.append(l)
+    else:
+        l['what'] = 'conv1_1 dgrad'; first.append(l)
+assert len(conv) == 24
 tot = sum(l['dram_read'] + l['dram_write'] for l in conv)
 print(json.dumps({
     'source': sys.argv[1], 'what': 'ncu --set full, one L-BFGS iteration at 1024x1024, tc_conv_kernel launches',
@@ -47,4 +63,5 @@ print(json.dumps({
     'conv3x3_tensor_pipe_pct_time_weighted': sum((l['tensor_pipe_pct'] or 0) * l['us_under_ncu'] for l in conv) /
     sum(l['us_under_ncu'] for l in conv),
     'style_grad_dram_bytes_per_iteration': sum(l['dram_read'] + l['dram_write'] for l in style),
+    'conv1_1_dgrad_dram_bytes': sum(l['dram_read'] + l['dram_write'] for l in first),
     'launches': launches}, indent=1))
