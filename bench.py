@@ -234,6 +234,10 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION; stdout carries the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     def barrier():
