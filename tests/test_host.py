@@ -201,3 +201,23 @@ def test_job_messages_follow_the_app_sequence_and_pickle():
     for msg in msgs + adam:
         back = pickle.loads(pickle.dumps(msg))
         assert type(back) is type(msg) and sorted(vars(back)) == sorted(vars(msg))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs the CPU port alone (no GPU, no libst2) and prints ONE JSON line with the
+    keys the driver reads: impl, metric, value, unit, config, cpu_baseline, e2e with zero copy bytes."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--size', '48',
+                          '--steps', '1', '--warmup', '1', '--cpu-budget', '1'], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'style-transfer iterations/sec' and d['unit'] == 'it/s'
+    assert d['value'] > 0 and d['higher_is_better'] is True and d['gpu_launches'] == 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config']
