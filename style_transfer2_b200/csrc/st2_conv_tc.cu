@@ -69,6 +69,15 @@ struct TileWalk {
   }
 };
 
+__device__ __forceinline__ uint4 shfl_xor_u4(const uint4& v, const int m) {
+  uint4 r;
+  r.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+  r.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+  r.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+  r.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+  return r;
+}
+
 // One 32-channel chunk of one output pixel: accumulator -> bias+ReLU | ReLU mask (+ loss injection) | raw
 // -> fp16 (saturating) -> four 16-byte stores.  a4 / s4: the pixel's 32 channels of the mask source and
 // of the style-gradient injection, already in registers.
@@ -76,7 +85,10 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
                                           const uint4 (&a4)[4], const uint4 (&s4)[4], const __half* __restrict__ fc_c,
                                           const bool have_inj, const bool have_s, const float cc, const float sc,
                                           const float dc, const float out_scale, const bool want_ss, float& ss,
-                                          __half* __restrict__ out_c, const int sw = 0) {
+                                          __half* __restrict__ out_c, const int sw = 0, const bool valid = true,
+                                          const long long pix_stride = 0) {
+  // Called by ALL lanes of the warp (shuffles inside); `valid` = this lane's pixel exists.  pix_stride = elements
+  // between horizontally adjacent pixels of the output (cout).
   // out_c: where this chunk's four 16-byte pieces go.  sw = 0: consecutive (global memory).  sw != 0: out_c is
   // a 128-byte row of a SWIZZLE_128B staging tile in shared memory, pieces q land at ((chunk0 + q) ^ row%8)
   // with chunk0 = sw >> 3 and row%8 = sw & 7 (bit 6 set marks the mode).
@@ -142,16 +154,42 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
       for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(out_c);
+  uint4 o4[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint4 o;
-    __half2* hp = reinterpret_cast<__half2*>(&o);
+    __half2* hp = reinterpret_cast<__half2*>(&o4[q]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
-    if (sw == 0) op[q] = o;
-    else op[(((sw >> 3) & 7) + q) ^ (sw & 7)] = o;
   }
+  if (sw != 0) {
+    uint4* op = reinterpret_cast<uint4*>(out_c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) op[(((sw >> 3) & 7) + q) ^ (sw & 7)] = o4[q];
+    return;
+  }
+  // Direct stores.  A lane holds 64 contiguous bytes of ITS pixel; storing them as they are makes every store
+  // instruction touch 32 different lines with 16 bytes each (measured: the epilogue then tops out at ~1.8 TB/s and
+  // bounds every layer with <= 128 output channels).  4 x 4 transpose of the 16-byte pieces inside each quad of
+  // lanes (quads = 4 horizontally adjacent pixels): afterwards slot j holds piece (lane & 3) of pixel quad + j, and
+  // store j writes 64 contiguous bytes per quad.
+  const int lane = threadIdx.x & 31, me = lane & 3;
+  {
+    const bool b0 = (lane & 1) != 0;
+    uint4 snd = b0 ? o4[0] : o4[1], rcv = shfl_xor_u4(snd, 1);
+    if (b0) o4[0] = rcv; else o4[1] = rcv;
+    snd = b0 ? o4[2] : o4[3]; rcv = shfl_xor_u4(snd, 1);
+    if (b0) o4[2] = rcv; else o4[3] = rcv;
+    const bool b1 = (lane & 2) != 0;
+    snd = b1 ? o4[0] : o4[2]; rcv = shfl_xor_u4(snd, 2);
+    if (b1) o4[0] = rcv; else o4[2] = rcv;
+    snd = b1 ? o4[1] : o4[3]; rcv = shfl_xor_u4(snd, 2);
+    if (b1) o4[1] = rcv; else o4[3] = rcv;
+  }
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if ((vmask >> ((lane & ~3) + j)) & 1u)
+      *reinterpret_cast<uint4*>(out_c + (long long)(j - me) * pix_stride + me * 8) = o4[j];
 }
 
 template <int BN>
@@ -325,10 +363,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t r[32];
           tc::tmem_ld_32x32(t_row + c * 32, r);
           tc::tmem_ld_wait();
-          if (valid)
-            epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
-                      (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                      out_scale, sumsq != nullptr, ss, out + obase + c * 32);
+          epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
+                    (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                    out_scale, valid && sumsq != nullptr, ss, out + obase + c * 32, 0, valid, g.cout);
         }
       } else {
 #pragma unroll 1
@@ -336,22 +373,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t r[32];
           tc::tmem_ld_32x32(t_row + c * 32, r);
           tc::tmem_ld_wait();
-          if (valid) {
-            uint4 a4[4], s4[4];
-            if (masked) {
-              const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
+          uint4 a4[4], s4[4];
+          if (valid && masked) {
+            const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) a4[q] = __ldg(ap + q);
-            }
-            if (have_s) {
-              const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) s4[q] = __ldg(sp + q);
-            }
-            epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
-                      (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                      out_scale, sumsq != nullptr, ss, out + obase + c * 32);
+            for (int q = 0; q < 4; ++q) a4[q] = __ldg(ap + q);
           }
+          if (valid && have_s) {
+            const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s4[q] = __ldg(sp + q);
+          }
+          epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
+                    (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                    out_scale, valid && sumsq != nullptr, ss, out + obase + c * 32, 0, valid, g.cout);
         }
       }
       tc::fence_before_sync();
@@ -535,10 +570,9 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           uint32_t r[32];
           tc::tmem_ld_32x32(t_row + c * 32, r);
           tc::tmem_ld_wait();
-          if (valid)
-            epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
-                      (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                      1.f, false, ss, out + obase + c * 32);
+          epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
+                    (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                    1.f, false, ss, out + obase + c * 32, 0, valid, g.cout);
         }
       }
 #pragma unroll 1
@@ -546,22 +580,20 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         uint32_t r[32];
         tc::tmem_ld_32x32(t_row + c * 32, r);
         tc::tmem_ld_wait();
-        if (valid) {
-          uint4 a4[4], s4[4];
-          if (masked) {
-            const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
+        uint4 a4[4], s4[4];
+        if (valid && masked) {
+          const uint4* ap = reinterpret_cast<const uint4*>(act + obase + c * 32);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) a4[q] = __ldg(ap + q);
-          }
-          if (have_s) {
-            const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s4[q] = __ldg(sp + q);
-          }
-          epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
-                    (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc, 1.f,
-                    false, ss, out + obase + c * 32);
+          for (int q = 0; q < 4; ++q) a4[q] = __ldg(ap + q);
         }
+        if (valid && have_s) {
+          const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s4[q] = __ldg(sp + q);
+        }
+        epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
+                  (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                  1.f, false, ss, out + obase + c * 32, 0, valid, g.cout);
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -866,10 +898,9 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t r[32];
         tc::tmem_ld_32x32(t_row + c * 32, r);
         tc::tmem_ld_wait();
-        if (valid)
-          epi_chunk(r, epi, bias + nb * BN + c * 32, pa[c], ps[c],
-                    (have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                    1.f, false, ss, out + obase + c * 32);
+        epi_chunk(r, epi, bias + nb * BN + c * 32, pa[c], ps[c],
+                  (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                  1.f, false, ss, out + obase + c * 32, 0, valid, g.cout);
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -883,6 +914,179 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 2) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ================================================================================================
+// Weight-stationary halo reuse AND CTA pair, for the 128-channel layers at half resolution (conv2_1 forward,
+// conv2_2 both directions): N = 128 split over the two CTAs of a pair (64 weight rows each, all 9 taps x KB
+// channel blocks resident: 72 / 144 KB), M = 256 = two 16 x 8 pixel tiles stacked vertically, each CTA
+// loading ONE 36 KB patch per tile and channel block.  The generic pair kernel moves 24 KB per CTA per
+// 256 MMA cycles from L2 for these layers (94 B/clk/SM -- the fill path, not the tensor pipe, was the limit:
+// ncu 38-52 % tensor active); here it is 36 KB per 2304 cycles.
+template <int KB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+tc_conv_wsp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
+                   __half* __restrict__ out, const int epi, const TcInject inj) {
+  constexpr int BN = 128;
+  constexpr int kWTile = (BN / 2) * 128;                       // this CTA's 64 rows of one tap, one channel block
+  constexpr int kWBytes = KB * 9 * kWTile;
+  constexpr int kStages = (KB == 1) ? 4 : 2;
+  constexpr int kTmemCols = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_p = smem + kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWBytes + kStages * kPatchBytes);
+  uint64_t* full_bar = bars;                         // leader's copy collects both CTAs' bytes
+  uint64_t* empty_bar = bars + kStages;              // local (multicast commit)
+  uint64_t* tmem_full = bars + 2 * kStages;          // local (multicast commit)
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;     // leader's copy: 4 local + 4 remote epilogue warps
+  uint64_t* w_full = bars + 2 * kStages + 4;         // leader's copy
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_tiles = g.tiles_h * g.tiles_w * g.n_blocks;      // tiles_h counts 32-row pair tiles
+  // a pair keeps one N block for its whole life (its weights are resident)
+  const int nb = pair % g.n_blocks;
+  const int pt0 = pair / g.n_blocks, pt_step = n_pairs / g.n_blocks;
+  const int n_pt = g.tiles_h * g.tiles_w;
+  (void)n_tiles;
+
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 8); }
+    tc::mbar_init(w_full, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc_2sm(tmem_slot, kTmemCols);
+  tc::fence_before_sync();
+  tc::cluster_sync_all();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (rank == 0 && tc::elect_one()) tc::mbar_expect_tx(w_full, 2u * kWBytes);
+    if (tc::elect_one()) {
+      for (int kb = 0; kb < KB; ++kb)
+        for (int tap = 0; tap < 9; ++tap)
+          tc::tma_load_2d_2sm(smem_w + (kb * 9 + tap) * kWTile, &tmap_b, w_full, tap * g.cin + kb * BK,
+                              nb * BN + (int)rank * (BN / 2));
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = pt0; pt < n_pt; pt += pt_step) {
+      const int th = pt / g.tiles_w, tw = pt - th * g.tiles_w;
+      const int h0 = th * (2 * kWsTH) + (int)rank * kWsTH, w0 = tw * kWsTW;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0 && tc::elect_one()) tc::mbar_expect_tx(&full_bar[stage], 2u * kPatchBytes);
+        if (tc::elect_one())
+          tc::tma_load_3d_2sm(smem_p + stage * kPatchBytes, &tmap_a, &full_bar[stage], kb * BK, w0 - 1, h0 - 1 + g.hoff);
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (leader only) ================================
+    constexpr uint32_t idesc = tc::idesc_f16(2 * BM, BN, 0, 0);
+    const uint32_t p_addr0 = tc::smem_u32(smem_p);
+    const uint64_t b_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_w));
+    tc::mbar_wait(w_full, 0);
+    tc::fence_after_sync();
+    int stage = 0; uint32_t phase = 0;
+    int local = 0;
+    for (int pt = pt0; pt < n_pt; pt += pt_step, ++local) {
+      const int acc = local & 1;
+      tc::mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t p_addr = p_addr0 + stage * kPatchBytes;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t a_desc = smem_desc_patch(p_addr + ((tap / 3) * kPatchW + (tap % 3)) * 128);
+            const uint64_t b_desc = b_desc0 + (uint64_t)(((kb * 9 + tap) * kWTile) >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | tap | k) != 0);
+          }
+          tc::umma_commit_2sm(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (tc::elect_one()) tc::umma_commit_2sm(&tmem_full[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ epilogue (both CTAs, own 16 x 8 pixels) =================
+    const int ew = warp - kEpiWarp0;
+    const int row = ew * 32 + lane;
+    const int row_h = row / kWsTW, row_w = row % kWsTW;
+    float ss = 0.f;
+    float cc = 0.f, sc = 0.f, dc = 0.f;
+    if (inj.coef != nullptr) { cc = (float)inj.coef[0]; sc = (float)inj.coef[1]; dc = (float)inj.coef[2]; }
+    constexpr int NCH = BN / 32;
+    const bool masked = (epi == EPI_MASK);
+    const bool have_inj = masked && inj.coef != nullptr;
+    const bool have_s = have_inj && inj.sraw != nullptr;
+    int local = 0;
+    for (int pt = pt0; pt < n_pt; pt += pt_step, ++local) {
+      const int acc = local & 1;
+      const int th = pt / g.tiles_w, tw = pt - th * g.tiles_w;
+      const int h = th * (2 * kWsTH) + (int)rank * kWsTH + row_h, w = tw * kWsTW + row_w;
+      const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
+      const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      uint4 pa[NCH][4], ps[NCH][4];
+      if (valid && masked) {
+        const uint4* ap = reinterpret_cast<const uint4*>(act + obase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pa[c][q] = __ldg(ap + c * 4 + q);
+      }
+      if (valid && have_s) {
+        const uint4* sp = reinterpret_cast<const uint4*>(inj.sraw + obase);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ps[c][q] = __ldg(sp + c * 4 + q);
+      }
+      if (lane == 0) tc::mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+      __syncwarp();
+      tc::fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(t_row + c * 32, r);
+        tc::tmem_ld_wait();
+        epi_chunk(r, epi, bias + nb * BN + c * 32, pa[c], ps[c],
+                  (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
+                  1.f, false, ss, out + obase + c * 32, 0, valid, g.cout);
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+
+  tc::fence_before_sync();
+  tc::cluster_sync_all();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 
@@ -989,8 +1193,22 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
     g.tiles_h = (H + g.TH - 1) / g.TH;
     g.tiles_w = (W + g.TW - 1) / g.TW;
   }
-  // ST2_FORCE_PAIR lets small test canvases reach the CTA-pair kernel (normally chosen by size)
+  // ST2_FORCE_PAIR lets small test canvases reach the CTA-pair kernels (normally chosen by size)
   const bool force_pair = getenv("ST2_FORCE_PAIR") != nullptr;
+  // weight-stationary + CTA pair for the 128-channel layers (conv2_1 forward, conv2_2): N = 128, cin <= 128
+  bool wsp = false;
+  if (!p->ws_kb && taps == 9 && cout == 128 && cin <= 128 && W >= 16 && H >= 32 && !getenv("ST2_NO_WSP") &&
+      !getenv("ST2_NO_PAIR")) {
+    const long long pair_tiles = (long long)((H + 31) / 32) * ((W + kWsTW - 1) / kWsTW);
+    if (pair_tiles >= ctx->sm_count / 2 || force_pair) {
+      wsp = true;
+      p->ws_kb = cin / 64;
+      p->bn = 128;
+      g.TW = kWsTW; g.TH = kWsTH;
+      g.tiles_h = (H + 31) / 32;
+      g.tiles_w = (W + kWsTW - 1) / kWsTW;
+    }
+  }
   if (force_pair && !p->ws_kb && taps == 9 && cout >= 128) p->bn = (cout % 256 == 0) ? 256 : 128;
   g.n_blocks = cout / p->bn;
   // CTA pairs for the wide layers when there is at least one wave of 16 x 16 pixel pair tiles
@@ -1004,6 +1222,7 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
       g.tiles_h = (H + 15) / 16;
     }
   }
+  if (wsp) p->pair = true;
   g.total_tiles = g.tiles_h * g.tiles_w * g.n_blocks;
   g.cblocks = cin / BK;
   g.k_iters = taps * g.cblocks;
@@ -1096,6 +1315,28 @@ static int launch_pair(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __h
   return 0;
 }
 
+template <int KB>
+static int launch_wsp(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
+                      const TcInject& inj) {
+  constexpr int kStages = (KB == 1) ? 4 : 2;
+  constexpr int smem = KB * 9 * 64 * 128 + kStages * kPatchBytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_wsp_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int nbk = p->g.n_blocks;
+  const int n_pt = p->g.tiles_h * p->g.tiles_w;
+  int per_nb = (ctx->sm_count / 2) / nbk;
+  if (per_nb > n_pt) per_nb = n_pt;
+  if (per_nb < 1) per_nb = 1;
+  p->g.dbg = ctx->debug_flags;
+  tc_conv_wsp_kernel<KB><<<2 * per_nb * nbk, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act, out,
+                                                                               epi, inj);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx) {
   if (!p || p->bn != 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
   TcInject inj;
@@ -1113,6 +1354,8 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     if (epi != EPI_MASK) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: injection needs the mask epilogue");
     inj = *inj_in;
   }
+  if (p->ws_kb && p->pair && out_scale == 1.f && sumsq == nullptr)
+    return p->ws_kb == 1 ? launch_wsp<1>(ctx, p, bias, act, out, epi, inj) : launch_wsp<2>(ctx, p, bias, act, out, epi, inj);
   if (p->ws_kb && out_scale == 1.f && sumsq == nullptr) {
     if (p->ws_kb == 1 && p->bn == 64) return launch_ws<64, 1>(ctx, p, bias, act, out, epi, inj);
     if (p->ws_kb == 1 && p->bn == 128) return launch_ws<128, 1>(ctx, p, bias, act, out, epi, inj);
@@ -1132,4 +1375,5 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
 static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>),
                                       ST2_KFN(tc_conv_ws_kernel<64, 1>), ST2_KFN(tc_conv_ws_kernel<128, 1>),
                                       ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>),
-                                      ST2_KFN(tc_conv2_kernel<256>), ST2_KFN(tc_conv2_kernel<128>)});
+                                      ST2_KFN(tc_conv2_kernel<256>), ST2_KFN(tc_conv2_kernel<128>),
+                                      ST2_KFN(tc_conv_wsp_kernel<1>), ST2_KFN(tc_conv_wsp_kernel<2>)});

