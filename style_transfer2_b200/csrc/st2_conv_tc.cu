@@ -1048,6 +1048,25 @@ tc_conv_wsp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int h = th * (2 * kWsTH) + (int)rank * kWsTH + row_h, w = tw * kWsTW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      if (masked) {
+        // next tile's mask / injection operands towards L2 (a tile is only ~2.4 us of MMA here, and the loads
+        // below are issued and then immediately needed)
+        const int ptn = pt + pt_step;
+        if (ptn < n_pt) {
+          const int thn = ptn / g.tiles_w, twn = ptn - thn * g.tiles_w;
+          const int hn = thn * (2 * kWsTH) + (int)rank * kWsTH + row_h, wn = twn * kWsTW + row_w;
+          if (hn < g.H && wn < g.W) {
+            const __half* an = act + ((long long)hn * g.W + wn) * g.cout + (long long)nb * BN;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(an));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(an + 64));
+            if (have_s) {
+              const __half* sn = inj.sraw + ((long long)hn * g.W + wn) * g.cout + (long long)nb * BN;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(sn));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + 64));
+            }
+          }
+        }
+      }
       uint4 pa[NCH][4], ps[NCH][4];
       if (valid && masked) {
         const uint4* ap = reinterpret_cast<const uint4*>(act + obase);
@@ -1197,7 +1216,10 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   const bool force_pair = getenv("ST2_FORCE_PAIR") != nullptr;
   // weight-stationary + CTA pair for the 128-channel layers (conv2_1 forward, conv2_2): N = 128, cin <= 128
   bool wsp = false;
-  if (!p->ws_kb && taps == 9 && cout == 128 && cin <= 128 && W >= 16 && H >= 32 && !getenv("ST2_NO_WSP") &&
+  // OPT-IN (ST2_WSP=1): measured at 1024^2 after the epilogue stores were fixed, it wins only conv2_2 forward
+  // (65.6 vs 71.3 us) and loses conv2_1 forward (55.8 vs 47.3) and conv2_2 data gradient (89.7 vs 82.4) to the
+  // generic kernels -- with 2.4 us of MMA per tile the epilogue (one tile of look-ahead) is what bounds it.
+  if (!p->ws_kb && taps == 9 && cout == 128 && cin <= 128 && W >= 16 && H >= 32 && getenv("ST2_WSP") &&
       !getenv("ST2_NO_PAIR")) {
     const long long pair_tiles = (long long)((H + 31) / 32) * ((W + kWsTW - 1) / kWsTW);
     if (pair_tiles >= ctx->sm_count / 2 || force_pair) {

@@ -112,7 +112,8 @@ def test_cta_pair_kernels_forced_on_small_canvases(monkeypatch):
     tr_ref = dict(ref.traces[-1].data)
     grad_ref = grad_ref.cpu().numpy()
     monkeypatch.setenv('ST2_FORCE_PAIR', '1')
-    m2 = B200Model(precision='fp16')                       # fresh plans: the knob is read at plan creation
+    monkeypatch.setenv('ST2_WSP', '1')                     # also the opt-in weight-stationary CTA-pair kernel
+    m2 = B200Model(precision='fp16')                       # fresh plans: the knobs are read at plan creation
     utils.set_default_engine(m2.engine)
     got = whole(m2, x0, content, style)
     loss, grad = got.opfunc(got.input)
