@@ -263,49 +263,50 @@ struct HaloPush {
   unsigned int* counters;
 };
 
-// grid (blocks, 2): y = 0 pushes up, y = 1 pushes down.  The last block of a direction to finish raises the flag.
-__global__ void halo_push_kernel(const HaloPush a) {
+// grid (blocks, 2): y = 0 pushes up, y = 1 pushes down; the last block of a direction to finish raises the flag
+// over there.  Block (0, 0) then also does this strip's own waiting: thread 0 for the strip above, thread 1 for the
+// strip below (one launch per exchange instead of a push + a wait kernel).
+__global__ void halo_exchange_kernel(const HaloPush a, const unsigned long long* wait_up,
+                                     const unsigned long long* wait_dn, int* err) {
   const int dir = blockIdx.y;
-  if (a.dst[dir] == nullptr) return;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  for (int sgm = 0; sgm < a.nseg; ++sgm) {
-    const unsigned char* sp = a.src[dir] + sgm * a.src_seg_stride;
-    unsigned char* dp = a.dst[dir] + sgm * a.dst_seg_stride[dir];
-    if ((a.seg_bytes & 15) == 0 && (((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
-      const uint4* s4 = reinterpret_cast<const uint4*>(sp);
-      uint4* d4 = reinterpret_cast<uint4*>(dp);
-      for (long long i = tid; i < (a.seg_bytes >> 4); i += nth) d4[i] = s4[i];
-    } else {
-      const unsigned int* s1 = reinterpret_cast<const unsigned int*>(sp);
-      unsigned int* d1 = reinterpret_cast<unsigned int*>(dp);
-      for (long long i = tid; i < (a.seg_bytes >> 2); i += nth) d1[i] = s1[i];
+  if (a.dst[dir] != nullptr) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (int sgm = 0; sgm < a.nseg; ++sgm) {
+      const unsigned char* sp = a.src[dir] + sgm * a.src_seg_stride;
+      unsigned char* dp = a.dst[dir] + sgm * a.dst_seg_stride[dir];
+      if ((a.seg_bytes & 15) == 0 && (((uintptr_t)sp | (uintptr_t)dp) & 15) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(sp);
+        uint4* d4 = reinterpret_cast<uint4*>(dp);
+        for (long long i = tid; i < (a.seg_bytes >> 4); i += nth) d4[i] = s4[i];
+      } else {
+        const unsigned int* s1 = reinterpret_cast<const unsigned int*>(sp);
+        unsigned int* d1 = reinterpret_cast<unsigned int*>(dp);
+        for (long long i = tid; i < (a.seg_bytes >> 2); i += nth) d1[i] = s1[i];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(&a.counters[dir], 1u);
+      if (prev == gridDim.x - 1) {
+        a.counters[dir] = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[dir]), "l"(a.epoch) : "memory");
+      }
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(&a.counters[dir], 1u);
-    if (prev == gridDim.x - 1) {
-      a.counters[dir] = 0;
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[dir]), "l"(a.epoch) : "memory");
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) {
+    const unsigned long long* f = threadIdx.x == 0 ? wait_up : wait_dn;
+    if (f == nullptr || *reinterpret_cast<volatile int*>(err) != 0) return;
+    unsigned long long t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= a.epoch) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) { atomicExch(err, 1); break; }     // 10 s: the neighbour died; fail loudly, don't hang
+      __nanosleep(64);
     }
-  }
-}
-
-// thread 0 waits for the strip above, thread 1 for the strip below (null = nobody there)
-__global__ void halo_wait_kernel(const unsigned long long* f_up, const unsigned long long* f_dn,
-                                 unsigned long long epoch, int* err) {
-  const unsigned long long* f = threadIdx.x == 0 ? f_up : f_dn;
-  if (f == nullptr || *reinterpret_cast<volatile int*>(err) != 0) return;
-  unsigned long long t0, t1, v;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-    if (v >= epoch) break;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 10000000000ull) { atomicExch(err, 1); break; }     // 10 s: the neighbour died; fail loudly, don't hang
-    __nanosleep(64);
   }
 }
 
@@ -413,10 +414,8 @@ static int halo_exchange(st2_plan* pl, int slot) {
   int blocks = (int)((vecs + 255) / 256);
   if (blocks < 1) blocks = 1;
   if (blocks > 32) blocks = 32;
-  halo_push_kernel<<<dim3(blocks, 2), 256, 0, ctx->stream>>>(a);
-  ST2_LAUNCH_CHECK(ctx);
-  halo_wait_kernel<<<1, 2, 0, ctx->stream>>>(up ? &mine->flag_from[0][slot] : nullptr,
-                                             dn ? &mine->flag_from[1][slot] : nullptr, epoch, &mine->err);
+  halo_exchange_kernel<<<dim3(blocks, 2), 256, 0, ctx->stream>>>(a, up ? &mine->flag_from[0][slot] : nullptr,
+                                                                 dn ? &mine->flag_from[1][slot] : nullptr, &mine->err);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1255,6 +1254,6 @@ int st2_gram_nchw(st2_ctx* ctx, const float* x, int C, long long HW, float* out)
 
 }  // extern "C"
 
-static St2KernelReg g_reg_net({ST2_KFN(halo_push_kernel), ST2_KFN(halo_wait_kernel), ST2_KFN(pack_x_kernel),
+static St2KernelReg g_reg_net({ST2_KFN(halo_exchange_kernel), ST2_KFN(pack_x_kernel),
                                   ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(scatter_sums_kernel),
                                   ST2_KFN(coef_kernel), ST2_KFN(final_kernel), ST2_KFN(pack_weights_kernel)});
