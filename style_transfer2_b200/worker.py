@@ -11,6 +11,7 @@ from collections import OrderedDict
 import ctypes as C
 import logging
 import math
+import pickle
 import sys
 import time
 
@@ -575,7 +576,11 @@ class Worker:
         handle, self._pending = self._pending, None
         if handle is not None:
             image, trace = handle.result()
-            self.sock_out.send_pyobj(Iterate(np.array(image), handle.t, dict(trace)))
+            # `image` is a view of a pinned double buffer: pickling copies it out right here, before the buffer can
+            # be reused, so no intermediate np.array() copy; one frame, as recv_pyobj on the app side expects
+            # (send_pyobj would pickle with the default protocol and then copy the 12.6 MB frame once more).
+            frame = pickle.dumps(Iterate(image, handle.t, dict(trace)), protocol=pickle.HIGHEST_PROTOCOL)
+            self.sock_out.send(frame, copy=False)
 
     def process_message(self, msg):
         """worker.py:366-409.  Returns True when the loop should end."""
