@@ -44,6 +44,8 @@ __device__ __forceinline__ float ipow(float m, int k) {
 //   tv_grad = gw + gh - gw(h, w-1) - gh(h-1, w)
 //   p_norm = sum |v|^p (the 1/p is applied by the caller); p_grad = sign(v)|v|^(p-1)
 //   grad = bwd + tv*tv_grad + p*p_grad
+constexpr int kPxRows = 8, kPxCols = 256;      // outputs per work item: 8 rows x 256 columns of one plane
+
 __global__ void __launch_bounds__(256)
 pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, float* __restrict__ grad, int C, int H,
                    int W, long long xps, int wrap, float tv, float beta, float pw, float pp, float divisor,
@@ -51,7 +53,10 @@ pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, f
   // x: row 0 of plane 0, planes xps floats apart.  wrap = 1: rows wrap around inside the tensor (whole
   // canvas); wrap = 0: rows -1 and H are addressable halo rows (a row strip; the strips at the canvas
   // edges hold the circular neighbours there).  bwd / grad are dense C x H x W.
-  // Work item = one row of one plane (no 64-bit divisions per element); a thread walks the row.
+  // Work item = 8 rows x 256 columns of one plane.  The (8 + 2) x (256 + 2) values v = x / 255 it needs are
+  // divided ONCE (IEEE division, as the reference's x / 255) into shared memory; every output then reads its 7
+  // neighbours from there (the previous version divided 7 times per output and was bound by that).
+  __shared__ float sv[kPxRows + 2][kPxCols + 2];
   const long long HW = (long long)H * W;
   const float half_beta = beta * 0.5f;
   const int m_norm = (half_beta == 1.0f) ? 1 : 2;
@@ -60,52 +65,68 @@ pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, f
   const int pi = (int)pp;
   const bool p_int = ((float)pi == pp) && pi >= 1 && pi <= 16;
   float s_tv = 0.f, s_p = 0.f, s_b = 0.f, s_t = 0.f, s_pg = 0.f, s_g = 0.f;
-  const int rows = C * H;
-  for (int rr = blockIdx.x; rr < rows; rr += gridDim.x) {
-    const int c = rr / H, h = rr - c * H;
+  const int bands = (H + kPxRows - 1) / kPxRows, chunks = (W + kPxCols - 1) / kPxCols;
+  const int items = C * bands * chunks;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int ch = item % chunks, band = (item / chunks) % bands, c = item / (chunks * bands);
+    const int h0 = band * kPxRows, w0 = ch * kPxCols;
     const float* xp = x + (long long)c * xps;
-    const int hd = (wrap && h + 1 == H) ? 0 : h + 1, hu = (wrap && h == 0) ? H - 1 : h - 1;
-    const float* r0 = xp + (long long)h * W;
-    const float* rd = xp + (long long)hd * W;
-    const float* ru = xp + (long long)hu * W;
-    const long long obase = (long long)c * HW + (long long)h * W;
-    for (int w = threadIdx.x; w < W; w += blockDim.x) {
-      const int wr = (w + 1 == W) ? 0 : w + 1, wl = (w == 0) ? W - 1 : w - 1;
-      // IEEE divisions: the reference evaluates tv_norm / p_norm on x / 255 (worker.py:283,287)
-      const float v = r0[w] / divisor, vr = r0[wr] / divisor, vl = r0[wl] / divisor, vd = rd[w] / divisor;
-      const float vu = ru[w] / divisor, vld = rd[wl] / divisor, vur = ru[wr] / divisor;
-      // this pixel
-      const float dw0 = v - vr, dh0 = v - vd;
-      const float n0 = dw0 * dw0 + dh0 * dh0 + 1e-8f;
-      const float k0 = half_beta * pow_beta(n0, e_k, m_k);
-      // left neighbour (h, w-1)
-      const float dw1 = vl - v, dh1 = vl - vld;
-      const float n1 = dw1 * dw1 + dh1 * dh1 + 1e-8f;
-      const float k1 = half_beta * pow_beta(n1, e_k, m_k);
-      // upper neighbour (h-1, w)
-      const float dw2 = vu - vur, dh2 = vu - v;
-      const float n2 = dw2 * dw2 + dh2 * dh2 + 1e-8f;
-      const float k2 = half_beta * pow_beta(n2, e_k, m_k);
-      float tg = 2.0f * dw0 * k0 + 2.0f * dh0 * k0;
-      tg -= 2.0f * dw1 * k1;
-      tg -= 2.0f * dh2 * k2;
-      s_tv += pow_beta(n0, half_beta, m_norm);
-      const float mag = fabsf(v);
-      float mp1;                                           // |v|^(p-1)
-      if (p_int) mp1 = ipow(mag, pi - 1); else mp1 = powf(mag, pp - 1.0f);
-      s_p += p_int ? mp1 * mag : powf(mag, pp);
-      const float sgn = (v > 0.f) ? 1.f : (v < 0.f ? -1.f : 0.f);
-      const float tgw = tv * tg;
-      const float pgw = pw * (sgn * mp1);
-      s_t = fmaf(tgw, tgw, s_t);
-      s_pg = fmaf(pgw, pgw, s_pg);
-      if (grad != nullptr) {
-        const float b = bwd ? bwd[obase + w] : 0.f;
-        float g = b + tgw;                                 // worker.py:295-297 order
-        g += pgw;
-        grad[obase + w] = g;
-        s_b = fmaf(b, b, s_b);
-        s_g = fmaf(g, g, s_g);
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kPxRows + 2) * (kPxCols + 2); i += blockDim.x) {
+      const int r = i / (kPxCols + 2), q = i - r * (kPxCols + 2);
+      int hh = h0 + r - 1, ww = w0 + q - 1;
+      float v = 0.f;
+      if (hh <= H && ww <= W) {                 // beyond the canvas (ragged last band / chunk): unused
+        if (ww < 0) ww = W - 1; else if (ww == W) ww = 0;              // columns always wrap (utils.py:232-254)
+        if (wrap) { if (hh < 0) hh = H - 1; else if (hh == H) hh = 0; }
+        v = xp[(long long)hh * W + ww] / divisor;
+      }
+      sv[r][q] = v;
+    }
+    __syncthreads();
+    const int w = w0 + threadIdx.x;
+    if (w < W) {
+#pragma unroll
+      for (int r = 0; r < kPxRows; ++r) {
+        const int h = h0 + r;
+        if (h >= H) break;
+        const int q = threadIdx.x + 1, rr = r + 1;
+        const float v = sv[rr][q], vr = sv[rr][q + 1], vl = sv[rr][q - 1], vd = sv[rr + 1][q], vu = sv[rr - 1][q];
+        const float vld = sv[rr + 1][q - 1], vur = sv[rr - 1][q + 1];
+        // this pixel
+        const float dw0 = v - vr, dh0 = v - vd;
+        const float n0 = dw0 * dw0 + dh0 * dh0 + 1e-8f;
+        const float k0 = half_beta * pow_beta(n0, e_k, m_k);
+        // left neighbour (h, w-1)
+        const float dw1 = vl - v, dh1 = vl - vld;
+        const float n1 = dw1 * dw1 + dh1 * dh1 + 1e-8f;
+        const float k1 = half_beta * pow_beta(n1, e_k, m_k);
+        // upper neighbour (h-1, w)
+        const float dw2 = vu - vur, dh2 = vu - v;
+        const float n2 = dw2 * dw2 + dh2 * dh2 + 1e-8f;
+        const float k2 = half_beta * pow_beta(n2, e_k, m_k);
+        float tg = 2.0f * dw0 * k0 + 2.0f * dh0 * k0;
+        tg -= 2.0f * dw1 * k1;
+        tg -= 2.0f * dh2 * k2;
+        s_tv += pow_beta(n0, half_beta, m_norm);
+        const float mag = fabsf(v);
+        float mp1;                                           // |v|^(p-1)
+        if (p_int) mp1 = ipow(mag, pi - 1); else mp1 = powf(mag, pp - 1.0f);
+        s_p += p_int ? mp1 * mag : powf(mag, pp);
+        const float sgn = (v > 0.f) ? 1.f : (v < 0.f ? -1.f : 0.f);
+        const float tgw = tv * tg;
+        const float pgw = pw * (sgn * mp1);
+        s_t = fmaf(tgw, tgw, s_t);
+        s_pg = fmaf(pgw, pgw, s_pg);
+        if (grad != nullptr) {
+          const long long o = (long long)c * HW + (long long)h * W + w;
+          const float b = bwd ? bwd[o] : 0.f;
+          float g = b + tgw;                                 // worker.py:295-297 order
+          g += pgw;
+          grad[o] = g;
+          s_b = fmaf(b, b, s_b);
+          s_g = fmaf(g, g, s_g);
+        }
       }
     }
   }
@@ -184,9 +205,9 @@ int pixel_terms_strip(st2_ctx* ctx, const float* x, long long xps, int wrap, con
                       int C, int H, int W, float tv, float tv_power, float p, float p_power, float divisor,
                       double* scal) {
   if (!ctx || !x || !scal || C < 1 || H < 1 || W < 1) return st2_fail(ctx, ST2_ERR_ARG, "st2_pixel_terms: bad arguments");
-  // one block per (plane, row) work item, at most 8 per SM: few blocks keep the 6 double atomics per block cheap
-  int blocks = C * H;
-  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  // at most 6 blocks per SM: few blocks keep the 6 double atomics per block cheap
+  int blocks = C * ((H + kPxRows - 1) / kPxRows) * ((W + kPxCols - 1) / kPxCols);
+  if (blocks > ctx->sm_count * 6) blocks = ctx->sm_count * 6;
   pixel_terms_kernel<<<blocks, kThreads, 0, ctx->stream>>>(x, bwd, grad_out, C, H, W, xps, wrap, tv, tv_power, p, p_power,
                                                            divisor, scal);
   ST2_LAUNCH_CHECK(ctx);
