@@ -189,7 +189,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--size', type=int, default=0)
-    ap.add_argument('--workload', default='jobs', choices=['jobs', 'canvas', 'serving'])
+    ap.add_argument('--workload', default='jobs', choices=['jobs', 'canvas', 'serving', 'multiscale'])
     ap.add_argument('--jobs', type=int, default=64, help='serving: number of independent jobs')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('ST2_PRECISION', 'fp16'))
@@ -244,6 +244,55 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.workload == 'multiscale':
+        # BASELINE config 3: Adam (step 10), stock initial_weights.yaml, stages 512 -> 1024 -> 2048 joined by the
+        # worker's SetImages(size, RESAMPLE, content) path (app.py:177-228, worker.py:154-160): the iterate and
+        # Adam's moments are Lanczos / bilinear-resampled on the device, normalisers persist across stages.
+        from style_transfer2_b200 import optimizers
+        from style_transfer2_b200.model import B200Model
+        from style_transfer2_b200.worker import StyleTransfer
+        yaml_weights = {'content': {'conv4_2': 0.08}, 'style': {k: 1 for k in STYLE_LAYERS[:4]}, 'deepdream': {}}
+        model = B200Model(gpu=local, precision=args.precision)
+        st = StyleTransfer(model)
+        st.optimizer_cls, st.step_size = optimizers.AdamOptimizer, 10
+        stages, out = (512, 1024, 2048), []
+        for k, ssize in enumerate(stages):
+            content, style, x0 = load_images(ssize)
+            t_sw = time.perf_counter()
+            if k == 0:
+                st.set_input(x0)
+                st.set_content(content)
+                st.set_style(style)
+                st.set_weights(yaml_weights, PARAMS)
+                assert st.start()
+            else:
+                st.resample_input((ssize, ssize))
+                st.set_content(content)
+            for _ in range(3):
+                st.step(fetch=False)
+            torch.cuda.synchronize()
+            switch_s = time.perf_counter() - t_sw
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                st.step(fetch=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            out.append({'canvas': [ssize, ssize], 'ms_per_step': ms, 'it_per_s': 1000.0 / ms,
+                        'stage_switch_s_incl_3_warmup_steps': switch_s, 'loss': float(st.traces[-1].loss)})
+        total_ms = sum(o['ms_per_step'] for o in out) * args.steps
+        if rank == 0:
+            print(json.dumps({'metric': 'style-transfer iterations/sec', 'value': len(stages) * args.steps / (total_ms / 1000.0),
+                              'unit': 'it/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': 3,
+                              'ms_per_step': total_ms / (len(stages) * args.steps), 'higher_is_better': True,
+                              'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16 operands / f32 accumulate', 'data': 'synthetic',
+                              'config': {'workload': 'config3: Adam step 10, stock YAML weights, stages 512->1024->2048 via the RESAMPLE path, %d iterations per stage' % args.steps},
+                              'stages': out, 'gpu_launches': model.engine.launches()}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     if args.workload == 'serving':
         # BASELINE config 5: --jobs independent 512 x 512 jobs fed as message sequences to the job scheduler,
