@@ -1239,7 +1239,11 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   if (!p->ws_kb && taps == 9 && p->bn >= 128 && g.TW == 16 && (p->bn == 256 || taps * (cin / BK) >= 18) &&
       !getenv("ST2_NO_PAIR")) {
     const long long pair_tiles = (long long)((H + 15) / 16) * g.tiles_w * g.n_blocks;
-    if (pair_tiles >= ctx->sm_count / 2 || force_pair) {
+    const char* min_env = getenv("ST2_PAIR_MIN_TILES");          // tuning experiments
+    // one full wave of pair tiles; N = 128 pays off from ~0.8 waves on (conv5_1 at 1024^2: 64 pair tiles on 74
+    // pairs, 26.8 -> 22.7 us), N = 256 does not (31.6 vs 26.8 us there)
+    const long long min_tiles = min_env ? atoll(min_env) : (p->bn == 128 ? (ctx->sm_count * 2) / 5 : ctx->sm_count / 2);
+    if (pair_tiles >= min_tiles || force_pair) {
       p->pair = true;
       g.tiles_h = (H + 15) / 16;
     }
