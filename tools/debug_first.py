@@ -1,3 +1,5 @@
+"""Element-wise comparison of the tensor-core conv1_1 kernels (sliding-window forward, N=16 data gradient) with the
+CUDA-core fp32 kernels they replaced (ST2_NO_TC_FIRST=1): forward within 1 fp16 ulp, data gradient 2e-4 relative."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -1,3 +1,7 @@
+"""Hardware experiment behind tc_conv_ws_kernel: conv1_2 with delta weights (one tap, identity over channels) so
+that the output must equal the shifted input; run with st2_debug_flags 0 / 32 it showed that the UMMA descriptor's
+base_offset must stay 0 for 128-byte-aligned starts inside a TMA-written SWIZZLE_128B patch (flag 32 has since been
+removed from the kernel; kept as the record of the method)."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

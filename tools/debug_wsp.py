@@ -1,3 +1,5 @@
+"""Element-wise comparison of the opt-in weight-stationary CTA-pair kernel (ST2_WSP=1) with the generic kernels on
+conv2_1 / conv2_2 forward."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -1,3 +1,5 @@
+"""cProfile of JobScheduler.run on one GPU (where does a job's set-up time go: plan creation, cudaFree, pinned
+allocations) -- the measurement that led to pooled plans and the pinned trace ring."""
 import cProfile, pstats, sys, os
 sys.path.insert(0, os.getcwd())
 import bench
