@@ -69,6 +69,20 @@ struct TileWalk {
   }
 };
 
+// fused 2x2/2 max-pool of a forward epilogue: p = this lane's pooled pixel (32 channels of it), vert = lane distance
+// of the pixel one row below (the tile width), writer = this lane is the top-left pixel of its window
+struct PoolOut { __half* p; int vert; bool writer; };
+
+__device__ __forceinline__ uint4 hmax_u4(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __half2* x = reinterpret_cast<const __half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+  __half2* z = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) z[e] = __hmax2(x[e], y[e]);
+  return r;
+}
+
 __device__ __forceinline__ uint4 shfl_xor_u4(const uint4& v, const int m) {
   uint4 r;
   r.x = __shfl_xor_sync(0xffffffffu, v.x, m);
@@ -86,7 +100,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
                                           const bool have_inj, const bool have_s, const float cc, const float sc,
                                           const float dc, const float out_scale, const bool want_ss, float& ss,
                                           __half* __restrict__ out_c, const int sw = 0, const bool valid = true,
-                                          const long long pix_stride = 0) {
+                                          const long long pix_stride = 0, const PoolOut po = PoolOut{nullptr, 0, false}) {
   // Called by ALL lanes of the warp (shuffles inside); `valid` = this lane's pixel exists.  pix_stride = elements
   // between horizontally adjacent pixels of the output (cout).
   // out_c: where this chunk's four 16-byte pieces go.  sw = 0: consecutive (global memory).  sw != 0: out_c is
@@ -160,6 +174,18 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
     __half2* hp = reinterpret_cast<__half2*>(&o4[q]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+  }
+  if (po.p != nullptr || po.vert != 0) {
+    // Caffe's ceil-mode 2x2/2 max pool of the post-ReLU output, first in registers: the window's other pixels sit in
+    // lanes l^1 (next column) and l^vert (next row); pixels beyond the canvas contribute 0, the neutral element
+    // of a max over post-ReLU values.  (po.vert != 0 is warp-uniform: every lane takes part in the shuffles.)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 m = valid ? o4[q] : make_uint4(0, 0, 0, 0);
+      m = hmax_u4(m, shfl_xor_u4(m, 1));
+      m = hmax_u4(m, shfl_xor_u4(m, po.vert));
+      if (po.writer && valid) reinterpret_cast<uint4*>(po.p)[q] = m;
+    }
   }
   if (sw != 0) {
     uint4* op = reinterpret_cast<uint4*>(out_c);
@@ -333,6 +359,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int w = tk.tw * g.TW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      const bool do_pool = (epi == EPI_BIAS_RELU) && inj.pool != nullptr;
+      __half* const pool_px = do_pool ? inj.pool + ((long long)(h >> 1) * inj.pool_wp + (w >> 1)) * g.cout + (long long)nb * BN
+                                      : nullptr;
+      const bool pool_writer = do_pool && !(lane & 1) && !(lane & g.TW);
+      const int pool_vert = do_pool ? g.TW : 0;
       // Operands of the epilogue that do not depend on the accumulator (ReLU-mask source, style-gradient
       // injection) are fetched BEFORE waiting for the MMAs of this tile on the narrow tiles: those layers
       // are memory-bound and a DRAM round trip per 32-channel chunk would otherwise serialise behind the wait.
@@ -365,7 +396,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc::tmem_ld_wait();
           epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
                     (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                    out_scale, valid && sumsq != nullptr, ss, out + obase + c * 32, 0, valid, g.cout);
+                    out_scale, valid && sumsq != nullptr, ss, out + obase + c * 32, 0, valid, g.cout,
+                    PoolOut{do_pool ? pool_px + c * 32 : nullptr, pool_vert, pool_writer});
         }
       } else {
 #pragma unroll 1
@@ -386,7 +418,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
                     (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                    out_scale, valid && sumsq != nullptr, ss, out + obase + c * 32, 0, valid, g.cout);
+                    out_scale, valid && sumsq != nullptr, ss, out + obase + c * 32, 0, valid, g.cout,
+                    PoolOut{do_pool ? pool_px + c * 32 : nullptr, pool_vert, pool_writer});
         }
       }
       tc::fence_before_sync();
@@ -541,6 +574,11 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int w = (pt % g.tiles_w) * g.TW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
+      const bool do_pool = (epi == EPI_BIAS_RELU) && inj.pool != nullptr;
+      __half* const pool_px = do_pool ? inj.pool + ((long long)(h >> 1) * inj.pool_wp + (w >> 1)) * g.cout + (long long)nb * BN
+                                      : nullptr;
+      const bool pool_writer = do_pool && !(lane & 1) && !(lane & g.TW);
+      const int pool_vert = do_pool ? g.TW : 0;
       // narrow tiles: epilogue operands fetched before the accumulator wait (see tc_conv_kernel)
       constexpr bool PF = (BN <= 128);
       uint4 pa[PF ? NCH : 1][4], ps[PF ? NCH : 1][4];
@@ -572,7 +610,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           tc::tmem_ld_wait();
           epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
                     (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                    1.f, false, ss, out + obase + c * 32, 0, valid, g.cout);
+                    1.f, false, ss, out + obase + c * 32, 0, valid, g.cout,
+                    PoolOut{do_pool ? pool_px + c * 32 : nullptr, pool_vert, pool_writer});
         }
       }
 #pragma unroll 1
@@ -593,7 +632,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         epi_chunk(r, epi, bias + nb * BN + c * 32, a4, s4,
                   (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
-                  1.f, false, ss, out + obase + c * 32, 0, valid, g.cout);
+                  1.f, false, ss, out + obase + c * 32, 0, valid, g.cout,
+                  PoolOut{do_pool ? pool_px + c * 32 : nullptr, pool_vert, pool_writer});
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -852,6 +892,9 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (warp == kEpiWarp0 && lane == 0) tc::bulk_wait_read<1>();
         tc::named_bar_sync(1, 128);
         __half* srow = reinterpret_cast<__half*>(stg + row * 128);
+        const bool do_pool = (epi == EPI_BIAS_RELU) && inj.pool != nullptr;
+        __half* const pool_px = do_pool ? inj.pool + ((long long)(h >> 1) * inj.pool_wp + (w >> 1)) * g.cout + (long long)nb * BN
+                                        : nullptr;
         if (masked) {
           // re-sort the coalesced pieces: piece j of lane l belongs to staging row (ew*4 + j/2)*8 + (j%2)*4 + l/8,
           // chunk l%8; afterwards every thread reads the eight chunks of its own row
@@ -880,7 +923,9 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tc::tmem_ld_wait();
           epi_chunk(r, epi, bias + nb * BN + c * 32, pa[c], ps[c],
                     (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc,
-                    dc, 1.f, false, ss, srow, 64 | ((c * 4) << 3) | (row & 7));
+                    dc, 1.f, false, ss, srow, 64 | ((c * 4) << 3) | (row & 7), valid, g.cout,
+                    PoolOut{do_pool ? pool_px + c * 32 : nullptr, do_pool ? kWsTW : 0,
+                            do_pool && !(lane & 1) && !(lane & kWsTW)});
         }
         tc::fence_before_sync();
         tc::fence_proxy_async_smem();
@@ -1366,19 +1411,27 @@ static int launch_wsp(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __ha
 int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx) {
   if (!p || p->bn != 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
   TcInject inj;
-  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr; inj.pool = nullptr; inj.pool_wp = 0;
   return launch_ws<16, 1>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
 }
 
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
-                   float out_scale, double* sumsq, const TcInject* inj_in) {
+                   float out_scale, double* sumsq, const TcInject* inj_in, bool* pooled) {
   if (epi == EPI_BIAS_RELU && !bias) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: bias required");
   if (epi == EPI_MASK && !act) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: act required");
   TcInject inj;
-  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr; inj.pool = nullptr; inj.pool_wp = 0;
+  if (pooled) *pooled = false;
   if (inj_in) {
-    if (epi != EPI_MASK) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: injection needs the mask epilogue");
+    if (epi != EPI_MASK && (inj_in->fc || inj_in->sraw || inj_in->coef))
+      return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: injection needs the mask epilogue");
     inj = *inj_in;
+    // the fused pool lives in the generic, CTA-pair and TMA-store weight-stationary epilogues
+    const bool can_pool = epi == EPI_BIAS_RELU && inj.pool != nullptr && pooled != nullptr && out_scale == 1.f &&
+                          sumsq == nullptr && !(p->ws_kb && p->pair) && !(p->ws_kb && !(p->ws_kb == 1 && p->bn == 64)) &&
+                          !getenv("ST2_NO_POOL_FUSION");
+    if (!can_pool) { inj.pool = nullptr; inj.pool_wp = 0; }
+    else *pooled = true;
   }
   if (p->ws_kb && p->pair && out_scale == 1.f && sumsq == nullptr)
     return p->ws_kb == 1 ? launch_wsp<1>(ctx, p, bias, act, out, epi, inj) : launch_wsp<2>(ctx, p, bias, act, out, epi, inj);

@@ -79,9 +79,11 @@ void tc_conv_plan_destroy(TcConvPlan* p);
 // epi per EPI_*; bias fp32 (EPI_BIAS_RELU); act fp16 NHWC (EPI_MASK); sumsq nullable (sum of fp32 outputs^2)
 // inj (EPI_MASK only): out = mask(acc) + coef[0] (act - fc) + coef[1] sraw + coef[2] act -- the loss diffs of
 // the blob below enter under its ReLU mask in the same pass (fc / sraw nullable; coef: 3 device doubles)
-struct TcInject { const __half* fc; const __half* sraw; const double* coef; };
+// pool / pool_wp (EPI_BIAS_RELU only): also write the 2x2/2 ceil-mode max-pool of the output (NHWC, pool_wp pixels
+// per row) from the same epilogue; *pooled (tc_conv_launch) tells whether the launched kernel did it
+struct TcInject { const __half* fc; const __half* sraw; const double* coef; __half* pool; int pool_wp; };
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
-                   float out_scale, double* sumsq, const TcInject* inj = nullptr);
+                   float out_scale, double* sumsq, const TcInject* inj = nullptr, bool* pooled = nullptr);
 // conv1_1 data gradient on the tensor cores: plan made with cin = 64, cout = 16 (the 3 image planes padded),
 // weights [16][tap'][64] fp16; writes fp32 NCHW (3 dense planes of H x W)
 int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx);

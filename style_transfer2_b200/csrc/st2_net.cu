@@ -434,6 +434,7 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
     int rc = halo_exchange(pl, 0);
     if (rc) return rc;
   }
+  bool pool_fused = false;
   for (int i = 1; i <= top; ++i) {
     Blob& cur = pl->b[i];
     Blob& below = pl->b[i - 1];
@@ -459,8 +460,15 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
         rc = launch_conv_exact(ctx, (const float*)below.act, ctx->wf32_fwd[ci], ctx->bias[ci], nullptr,
                                (float*)cur.act, cur.H, cur.W, below.C, cur.C, EPI_BIAS_RELU, lo, hi);
       } else {
-        rc = tc_conv_launch(ctx, cur.tc_fwd, ctx->bias[ci], nullptr, (__half*)cur.act, EPI_BIAS_RELU, 1.f, nullptr);
+        // a max-pool right above this convolution is computed by the same epilogue when the kernel supports it
+        TcInject ti;
+        ti.fc = nullptr; ti.sraw = nullptr; ti.coef = nullptr; ti.pool = nullptr; ti.pool_wp = 0;
+        if (i + 1 <= top && g_blobs[i + 1].kind == KIND_POOL) { ti.pool = (__half*)pl->b[i + 1].act; ti.pool_wp = pl->b[i + 1].W; }
+        rc = tc_conv_launch(ctx, cur.tc_fwd, ctx->bias[ci], nullptr, (__half*)cur.act, EPI_BIAS_RELU, 1.f, nullptr, &ti,
+                            &pool_fused);
       }
+    } else if (pool_fused) {
+      pool_fused = false;                       // written by the convolution below
     } else {
       rc = launch_pool_fwd_v<T>(ctx, (const T*)below.act, (T*)cur.act, below.C, below.H, below.W);
     }
@@ -523,6 +531,7 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
       } else if (below_conv && inj[i - 1].on && inj[i - 1].coef != nullptr && !getenv("ST2_NO_FUSED_INJECT")) {
         TcInject ti;
         ti.fc = (const __half*)inj[i - 1].fc; ti.sraw = (const __half*)inj[i - 1].sraw; ti.coef = inj[i - 1].coef;
+        ti.pool = nullptr; ti.pool_wp = 0;
         rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad, EPI_MASK, 1.f,
                             nullptr, &ti);
         fused_inj = true;
