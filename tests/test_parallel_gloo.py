@@ -75,3 +75,55 @@ def test_single_process_fallbacks():
     assert parallel.all_max(3.5) == 3.5
     assert parallel.all_sum(2) == 2.0
     assert parallel.gather_objects({'a': 1}) == [{'a': 1}]
+
+
+def _strip_worker(rank, world, port, out_dir):
+    """The reduction protocol of the row-strip tiling (tiled.py / DESIGN section 6) on the CPU: every rank holds a
+    strip of rows, swaps ONE circular halo row of x with its neighbours, computes its partial sums with the oracle's
+    own formulas and all-reduces them -- the totals must be the whole canvas' values."""
+    import numpy as np
+    from oracle import numeric as nm
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(5)
+        H, W, C = 48, 20, 6
+        x = rs.randn(1, 3, H, W) * 40
+        F = np.maximum(rs.randn(1, C, H, W), 0)            # a post-ReLU "feature map" and its content target
+        Fc = np.maximum(rs.randn(1, C, H, W), 0)
+        r0, r1 = parallel.strip_bounds(H, world)[rank]
+        up, dn = (rank - 1) % world, (rank + 1) % world    # circular: the TV term wraps around the canvas
+        mine = torch.from_numpy(np.ascontiguousarray(x[:, :, r0:r1]))
+        halo_dn, halo_up = torch.empty(1, 3, 1, W, dtype=mine.dtype), torch.empty(1, 3, 1, W, dtype=mine.dtype)
+        ops = [dist.P2POp(dist.isend, mine[:, :, :1].contiguous(), up), dist.P2POp(dist.isend, mine[:, :, -1:].contiguous(), dn),
+               dist.P2POp(dist.irecv, halo_dn, dn), dist.P2POp(dist.irecv, halo_up, up)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        # TV partial: forward differences need the row BELOW the strip's last row (circular)
+        xs = np.concatenate([mine.numpy(), halo_dn.numpy()], axis=2) / 255.0
+        dw = xs[:, :, :-1] - np.roll(xs[:, :, :-1], -1, axis=3)
+        dh = xs[:, :, :-1] - xs[:, :, 1:]
+        tv_part = np.sum(dw ** 2 + dh ** 2 + 1e-8)          # beta = 2
+        Fs = F[0, :, r0:r1].reshape(C, -1)
+        sums = torch.tensor([tv_part, np.sum((F[:, :, r0:r1] - Fc[:, :, r0:r1]) ** 2), np.sum(F[:, :, r0:r1] ** 2)],
+                            dtype=torch.float64)
+        gram = torch.from_numpy(Fs @ Fs.T)                  # un-normalised strip Gram sum
+        dist.all_reduce(sums)
+        dist.all_reduce(gram)
+        want_tv, _ = nm.total_variation(x / 255.0, 2)
+        Fw = F[0].reshape(C, -1)
+        assert np.isclose(sums[0].item(), want_tv, rtol=1e-12)
+        assert np.isclose(sums[1].item(), np.sum((F - Fc) ** 2), rtol=1e-12)
+        assert np.isclose(sums[2].item(), np.sum(F ** 2), rtol=1e-12)
+        np.testing.assert_allclose(gram.numpy() / (C * H * W), Fw @ Fw.T / (C * H * W), rtol=1e-12)
+        with open(os.path.join(out_dir, 's%d.txt' % rank), 'w') as f:
+            f.write('ok %d %d' % (r0, r1))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_strip_reductions_reproduce_the_whole_canvas_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_strip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / ('s%d.txt' % r)).read() for r in range(2)] == ['ok 0 32', 'ok 32 48']
