@@ -180,7 +180,11 @@ class TiledJob:
         self.tt.step(fetch=False)
         if not fetch:
             return None, None
-        return None, self.tt.traces[-1].data          # the iterate's rows are read back by the caller
+        tr = self.tt.traces[-1]
+        data = tr.data                                # the iterate's rows are read back by the caller
+        if tr.halo_timeout():
+            raise RuntimeError('halo exchange timed out')
+        return None, data
 
 
 def main():

@@ -434,7 +434,10 @@ class TiledTransfer:
         tr('fevals', self.t)
         if not fetch:
             return None, None
-        return self.image(), tr.data
+        data = tr.data                       # waits for this evaluation's scalar block
+        if tr.halo_timeout():
+            raise RuntimeError('a halo exchange timed out: a neighbouring strip stopped (rank %d)' % self.strips[0].rank)
+        return self.image(), data
 
     # ------------------------------------------------------------------ results
     def gather(self, per_strip):
