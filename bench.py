@@ -13,9 +13,11 @@ N > 1: one process per GPU (torchrun), every rank runs an independent job of the
 (job-level data parallelism, no data-path collective) -> weak scaling; value = all ranks' iterations
 / max-over-ranks device time.
 
-``--workload canvas`` (BASELINE config 4): ONE --size x --size canvas (default 4096) split into row
-strips over the N GPUs (style_transfer2_b200/tiled.py: halo rows over peer memory, four small NCCL
-all-reduces per iteration) -> strong scaling; value = iterations of the whole canvas per second.
+Every line also carries a ``canvas`` record = BASELINE config 4 at this N: ONE 4096 x 4096 canvas, on
+one GPU as a whole-canvas plan, on N > 1 GPUs split into row strips (style_transfer2_b200/tiled.py:
+halo rows over peer memory, small NCCL all-reduces), with its own clocks, per-category times (incl.
+``halo`` and ``allreduce``), the one-GPU figure measured in the same run on rank 0 and the strips'
+parity against the CPU oracle at 1024^2.  ``--workload canvas`` makes that the headline value.
 
 One JSON line on stdout (rank 0).
 """
@@ -39,22 +41,50 @@ PARAMS = {'p': 50, 'p_power': 6, 'tv': 5, 'tv_power': 2}
 CONV_CH = [(3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256), (256, 256), (256, 256), (256, 512),
            (512, 512), (512, 512), (512, 512), (512, 512)]           # conv1_1 .. conv5_1
 CONV_POOL_BEFORE = [0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4]
+HISTORY_PREFILL = 10          # L-BFGS steps run at job set-up so that every timed step carries the full m = 10 history
 
 
 def pool_extent(n):
     return (n - 2 + 1) // 2 + 1 if n > 1 else 1
 
 
-def conv_flops(h, w, first=0, last=12):
-    """Algorithmic conv flops of one direction, layers first..last (18 Cin Cout H_l W_l each)."""
-    dims, total = [(h, w)], 0
+def level_dims(h, w):
+    dims = [(h, w)]
     for _ in range(4):
         dims.append((pool_extent(dims[-1][0]), pool_extent(dims[-1][1])))
+    return dims
+
+
+def conv_flops(h, w, first=0, last=12):
+    """Algorithmic conv flops of one direction, layers first..last (18 Cin Cout H_l W_l each)."""
+    dims, total = level_dims(h, w), 0
     for i in range(first, last + 1):
         cin, cout = CONV_CH[i]
         hh, ww = dims[CONV_POOL_BEFORE[i]]
         total += 18 * cin * cout * hh * ww
     return total
+
+
+def algorithmic_bytes(h, w, esz=2, m=10):
+    """Algorithmic HBM bytes per iteration of the bandwidth-bound kernel categories for the
+    config-2 objective (style conv1_1..conv5_1, content conv4_2) with activations of `esz` bytes."""
+    dims = level_dims(h, w)
+    n = 3 * h * w
+    style = [(c, dims[i][0] * dims[i][1]) for i, c in enumerate((64, 128, 256, 512, 512))]
+    gram = sum(c * hw * esz for c, hw in style)                                   # F read once per style layer
+    # style gradient (G - A) F: read F, write the raw gradient.  conv1_1's is produced inside conv1_2's data-gradient
+    # kernel when the fused path is on; the bytes are counted here either way (the category then shows less time)
+    style_grad = 2 * gram
+    conv_first = (4 * n + 64 * h * w * esz) * 2                                   # fwd: x -> conv1_1; dgrad: back
+    pool = 0
+    for lvl, c in enumerate((64, 128, 256, 512)):                                 # pool1..pool4 backward
+        below, pooled = dims[lvl][0] * dims[lvl][1], dims[lvl + 1][0] * dims[lvl + 1][1]
+        pool += c * esz * (2 * below + pooled)
+    optimizer = 2 * (2 * m + 4) * 4 * n                                           # compact L-BFGS: two passes
+    pixel = 12 * n
+    loss = 2 * 512 * dims[3][0] * dims[3][1] * esz + 3 * 512 * dims[4][0] * dims[4][1] * esz
+    return {'gram': gram, 'style_grad': style_grad, 'conv_first': conv_first, 'pool': pool, 'optimizer': optimizer,
+            'pixel_terms': pixel, 'loss_elementwise': loss}
 
 
 def load_images(size):
@@ -68,7 +98,7 @@ def load_images(size):
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of the profiling recipe, sampled during the timed region."""
+    """nvidia-smi clocks line of the profiling recipe, sampled every 20 ms from before the warm-up on."""
 
     def __init__(self, index):
         q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -87,13 +117,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
+        """Clocks over [t0, t1] (perf_counter); the sampler keeps running."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        # samples inside the timed region; the sampler runs from before the warm-up, so if the region was
-        # shorter than a sampling period fall back to the samples taken under the same load just around it
+        # samples inside the region; if it was shorter than a sampling period fall back to the samples taken under
+        # the same load just around it
         rows = ([r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or
                 [r for t, r in self.rows if t0 - 0.25 <= t <= t1 + 0.25 and len(r) >= 7] or
                 [r for _, r in self.rows if len(r) >= 7])
@@ -105,16 +134,34 @@ class ClockSampler:
         return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons,
                 'samples': len(rows), 'power_w_max': max(float(r[2]) for r in rows)}
 
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+def regime_of(clocks):
+    """'burst' when the timed region ran at >= 95 % of the maximum SM clock without a power cap, else 'sustained':
+    decides which measured bf16 peak the tensor-core roofline is divided by."""
+    if not clocks or not clocks.get('sm_mhz') or not clocks.get('sm_max_mhz'):
+        return 'sustained'
+    if clocks['sm_mhz'] >= 0.95 * clocks['sm_max_mhz'] and 'sw_power_cap' not in clocks.get('reasons', []):
+        return 'burst'
+    return 'sustained'
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
 
 # ------------------------------------------------------------------------------------ CPU arm
-def run_cpu_reference(size, steps, warmup, budget_s, full_net=True):
-    """The reference's CPU path restated (oracle/): StyleTransfer + L-BFGS + Caffe-CPU layer
-    semantics on torch-CPU fp32 with all host threads.  Returns (it/s, cores, sample description)."""
+def oracle_job(size, full_net=True):
     import torch
     from oracle.caffe_cpu import CaffeCPUModel
     from oracle.transfer import Transfer
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(os.cpu_count() or 1)
     content, style, x0 = load_images(size)
     st = Transfer(CaffeCPUModel(full_net=full_net))
     st.set_input(x0)
@@ -122,6 +169,22 @@ def run_cpu_reference(size, steps, warmup, budget_s, full_net=True):
     st.set_style(style)
     st.set_weights(WEIGHTS, PARAMS)
     assert st.start()
+    return st
+
+
+def oracle_first_eval(st):
+    """The objective at x0 on the CPU oracle: what the GPU arm's first evaluation is checked against."""
+    loss0, grad0 = st.opfunc(st.input)
+    return {'loss': float(loss0), 'grad': grad0.copy(), 'trace': dict(st.traces[-1].data)}
+
+
+def run_cpu_reference(size, steps, warmup, budget_s, full_net=True, first_eval=False):
+    """The reference's CPU path restated (oracle/): StyleTransfer + L-BFGS + Caffe-CPU layer
+    semantics on torch-CPU fp32 with all host threads.  Returns (it/s, cores, sample description, steps timed,
+    first evaluation or None)."""
+    cores = os.cpu_count() or 1
+    st = oracle_job(size, full_net)
+    first = oracle_first_eval(st) if first_eval else None
     t_begin = time.perf_counter()
     for _ in range(max(warmup, 1)):          # first step carries the extra evaluation at x0
         st.step()
@@ -137,11 +200,35 @@ def run_cpu_reference(size, steps, warmup, budget_s, full_net=True):
     its = len(times) / sum(times)
     sample = '%d timed L-BFGS steps of the %dx%d workload after %d warm-up (oracle: full net to pool5, no wgrad)' % (
         len(times), size, size, max(warmup, 1))
-    return its, cores, sample, len(times)
+    return its, cores, sample, len(times), first
+
+
+def parity_of(gpu_first, cpu_first):
+    """Relative errors of the GPU arm's first objective evaluation against the CPU oracle's on the same inputs."""
+    tr, want = gpu_first['trace'], cpu_first['trace']
+    worst, worst_key = 0.0, None
+    worst_l, worst_l_key = 0.0, None
+    for k, v in want.items():
+        if k == 'time' or k not in tr:
+            continue
+        err = abs(tr[k] - v) / max(abs(v), 1e-30)
+        if err > worst:
+            worst, worst_key = err, k
+        if not k.endswith('grad') and err > worst_l:
+            worst_l, worst_l_key = err, k
+    g, gw = np.asarray(gpu_first['grad'], np.float64), np.asarray(cpu_first['grad'], np.float64)
+    return {'loss_rel': abs(gpu_first['loss'] - cpu_first['loss']) / abs(cpu_first['loss']),
+            'worst_trace_rel': worst, 'worst_trace_key': worst_key,
+            'worst_loss_trace_rel': worst_l, 'worst_loss_trace_key': worst_l_key,
+            'grad_rel': float(np.linalg.norm((g - gw).ravel()) / np.linalg.norm(gw.ravel())),
+            'against': 'CPU oracle (oracle/: reference StyleTransfer restated + Caffe-CPU layer semantics, fp32), '
+                       'first objective evaluation at x0 on the same inputs',
+            'bound': 'losses and every *_loss trace value <= 1e-3 (north_star); *_grad values are RMS of gradients that '
+                     'are discontinuous in the features (ReLU masks, pool arg-max): <= 5e-2 in fp16'}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def build_job(size, precision, seed_shift=0):
+def build_job(size, precision, seed_shift=0, prefill=HISTORY_PREFILL, want_first=False):
     from style_transfer2_b200.model import B200Model
     from style_transfer2_b200.worker import StyleTransfer
     content, style, x0 = load_images(size)
@@ -154,23 +241,38 @@ def build_job(size, precision, seed_shift=0):
     st.set_style(style)
     st.set_weights(WEIGHTS, PARAMS)
     assert st.start()
-    return st
+    first = None
+    if want_first:
+        loss, grad = st.opfunc(st.input)
+        first = {'loss': float(loss), 'grad': grad.cpu().numpy(), 'trace': dict(st.traces[-1].data)}
+    for _ in range(prefill):
+        st.step(fetch=False)
+    return st, first
 
 
 class TiledJob:
     """The same step()/input surface as StyleTransfer for one row-tiled canvas (this rank's strip)."""
 
-    def __init__(self, size, precision):
+    def __init__(self, size, precision, model=None, prefill=HISTORY_PREFILL, want_first=False):
         from style_transfer2_b200.model import B200Model
         from style_transfer2_b200.tiled import TiledTransfer
         content, style, x0 = load_images(size)
-        model = B200Model(gpu=int(os.environ.get('LOCAL_RANK', 0)), precision=precision)
+        if model is None:
+            model = B200Model(gpu=int(os.environ.get('LOCAL_RANK', 0)), precision=precision)
         self.tt = TiledTransfer(model, size, size)
         self.tt.set_input(x0)
         self.tt.set_content(content)
         self.tt.set_style(style)
         self.tt.set_weights(WEIGHTS, PARAMS)
         self.engine = model.engine
+        self.first = None
+        if want_first:
+            loss, grads = self.tt.opfunc()
+            grad = self.tt.gather(grads)
+            self.first = {'loss': float(loss), 'trace': dict(self.tt.traces[-1].data),
+                          'grad': grad.cpu().numpy() if grad is not None else None}
+        for _ in range(prefill):
+            self.tt.step(fetch=False)
 
     @property
     def input(self):
@@ -186,6 +288,176 @@ class TiledJob:
             raise RuntimeError('halo exchange timed out')
         return None, data
 
+    def close(self):
+        self.tt.close()
+
+
+def profile_categories(eng, step, n, extra=None):
+    """Per-category device time (CUDA events on the launch stream, st2_profile) over n steps."""
+    import ctypes as C
+    from style_transfer2_b200 import _lib
+    eng.call('st2_profile', 1)
+    for _ in range(n):
+        step()
+    ms_cat = (C.c_double * _lib.PROF_CATS)()
+    n_cat = (C.c_longlong * _lib.PROF_CATS)()
+    eng.call('st2_profile_read', ms_cat, n_cat)
+    eng.call('st2_profile', 0)
+    cats = {name: {'ms_per_step': ms_cat[i] / n, 'launch_spans_per_step': n_cat[i] / n}
+            for i, name in enumerate(_lib.PROF_NAMES) if n_cat[i]}
+    if extra:
+        cats.update(extra(n))
+    return cats
+
+
+def rooflines_of(cats, size, share, peaks, regime, precision, canvas=False):
+    """The dominant tensor-core family first (the line's `roofline`), then one entry per bandwidth-bound category."""
+    out = []
+    burst, sustained = peaks.get('bf16_tflops', 1650.0), peaks.get('bf16_tflops_sustained', 1400.0)
+    hbm = peaks.get('hbm_gbs', 6500.0)
+    src = 'MEASURED_PEAKS.json' if peaks else 'fallback (B200_PROFILING.md)'
+    key = 'conv_tc' if 'conv_tc' in cats else ('conv_exact' if 'conv_exact' in cats else None)
+    main = None
+    if key:
+        fl = 2 * conv_flops(size, size, first=1) / share          # conv1_2..conv5_1, fwd + dgrad, this GPU's share
+        t_s = cats[key]['ms_per_step'] / 1000.0
+        ach = fl / t_s / 1e12
+        peak = burst if regime == 'burst' else sustained
+        traffic, traffic_src = None, None
+        if key == 'conv_tc' and size == 1024 and not canvas:
+            import glob
+            found = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_tcconv_traffic.json')))
+            if found:
+                tj = json.load(open(found[-1]))
+                traffic, traffic_src = tj['conv3x3_dram_bytes_per_launch'], os.path.relpath(found[-1], ROOT)
+        n_launch = cats[key]['launch_spans_per_step']
+        main = {'kernel': 'tcgen05 3x3 implicit-GEMM convolutions conv1_2..conv5_1, fwd + dgrad (tc_conv2_kernel / '
+                          'tc_conv_ws_kernel / tc_conv_kernel)' if key == 'conv_tc' else 'conv_exact_kernel (CUDA-core fp32)',
+                'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                'regime': regime, 'frac_of_burst_peak': ach / burst, 'frac_of_sustained_peak': ach / sustained,
+                'peak_source': '%s %s (clock regime observed by the sampler during the timed region: %s)' % (
+                    src, 'bf16_tflops' if regime == 'burst' else 'bf16_tflops_sustained', regime),
+                'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
+                'traffic_source': traffic_src, 'launches_per_step': n_launch,
+                'flops_per_launch': fl / n_launch if n_launch else None,
+                'avg_launch_ms': cats[key]['ms_per_step'] / n_launch if n_launch else None,
+                'flops_per_step': fl, 'ms_per_step': cats[key]['ms_per_step']}
+        out.append(main)
+    esz = 2 if precision != 'fp32' else 4
+    ab = algorithmic_bytes(size, size, esz)
+    names = {'gram': 'tc_gram_kernel (tcgen05 F^T F, split-K)', 'style_grad': 'style gradient (G - A) F (tc_conv_kernel taps = 1)',
+             'conv_first': 'conv1_1 fwd + dgrad (tc_conv_first_fwd_kernel, tc_conv_ws_kernel<16,1>)',
+             'pool': 'pool backward (pool_bwd_vec_kernel; forward pools live in the conv epilogues)',
+             'optimizer': 'compact L-BFGS (lbfgs_pass_a/b, coefficients, accept)', 'pixel_terms': 'pixel_terms_kernel (TV + p-norm + assembly)',
+             'loss_elementwise': 'feature sums / coefficients / top-layer combine'}
+    for cat, nbytes in ab.items():
+        if cat not in cats or not cats[cat]['ms_per_step']:
+            continue
+        b = nbytes / share
+        ach = b / (cats[cat]['ms_per_step'] / 1000.0) / 1e9
+        out.append({'kernel': names[cat], 'category': cat, 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
+                    'frac': ach / hbm, 'algorithmic_bytes_per_step': b, 'ms_per_step': cats[cat]['ms_per_step'],
+                    'launch_spans_per_step': cats[cat]['launch_spans_per_step'], 'traffic': None,
+                    'peak_source': '%s hbm_gbs' % src})
+    return main, out
+
+
+def timed_steps(st, steps, barrier, world, eng):
+    """K steps bracketed by barrier + synchronize, CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    barrier()
+    l0 = eng.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        st.step(fetch=False)
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, eng.launches() - l0, t0, t1
+
+
+def canvas_record(args, rank, world, local, sampler, peaks, barrier):
+    """BASELINE config 4 at this N: one 4096^2 canvas (N = 1: whole-canvas plan; N > 1: row strips)."""
+    import torch
+    size = args.canvas_size
+    steps, warm = max(5, min(args.steps, 20)), max(args.warmup, 3)
+    rec = {'workload': 'config4: one %dx%d canvas, config-2 weights, L-BFGS m=10, %s' % (
+        size, size, 'whole-canvas plan on one GPU' if world == 1 else 'row strips over %d GPUs (halo rows over peer memory, '
+        'NCCL sum all-reduces)' % world), 'n_gpus': world, 'steps': steps, 'warmup': warm, 'history_prefill_steps': HISTORY_PREFILL}
+    if world == 1:
+        job, _ = build_job(size, args.precision)
+        spans = None
+    else:
+        job = TiledJob(size, args.precision)
+        spans = []
+    eng = job.engine
+    for _ in range(warm):
+        job.step(fetch=False)
+    ms, launches, t0, t1 = timed_steps(job, steps, barrier, world, eng)
+    clocks = sampler.window(t0, t1) if sampler else None
+    rec.update(value=steps / (ms / 1000.0), unit='it/s', ms_per_step=ms / steps, gpu_launches_per_step=launches / steps,
+               clocks=clocks)
+
+    def extra(n):
+        if spans is None:
+            return {}
+        torch.cuda.synchronize()
+        tot = sum(a.elapsed_time(b) for a, b in spans)
+        cnt = len(spans)
+        del spans[:]
+        return {'allreduce': {'ms_per_step': tot / n, 'launch_spans_per_step': cnt / n,
+                              'note': 'NCCL sum all-reduces incl. waiting for the slowest rank'}}
+
+    if spans is not None:
+        job.tt.allreduce_spans = spans
+    cats = profile_categories(eng, lambda: job.step(fetch=False), min(steps, 10), extra)
+    if spans is not None:
+        job.tt.allreduce_spans = None
+    regime = regime_of(clocks)
+    main, roofs = rooflines_of(cats, size, world, peaks, regime, args.precision, canvas=True)
+    rec.update(kernel_time_ms_per_step=cats, roofline=main)
+    if rank == 0 and hasattr(job, 'traces'):
+        rec['loss'] = float(job.traces[-1].loss)
+    if world > 1:
+        if hasattr(job, 'close'):
+            job.close()
+        del job
+        torch.cuda.empty_cache()
+        # the one-GPU figure of the same canvas, measured in this run on rank 0 while the other ranks idle, so the
+        # efficiency compares like with like (same box, clocks recorded for both arms)
+        barrier()
+        if rank == 0:
+            one, _ = build_job(size, args.precision)
+            for _ in range(warm):
+                one.step(fetch=False)
+            ms1, _, t0, t1 = timed_steps(one, steps, lambda: torch.cuda.synchronize(), 1, one.engine)
+            c1 = sampler.window(t0, t1) if sampler else None
+            rec['one_gpu'] = {'ms_per_step': ms1 / steps, 'value': steps / (ms1 / 1000.0), 'clocks': c1}
+            rec['efficiency_vs_one_gpu_same_run'] = (ms1 / steps) / (world * ms / steps)
+            one.close()
+            del one
+            torch.cuda.empty_cache()
+        barrier()
+        # strips against the CPU ORACLE (not the un-split plan) at a size the oracle finishes in seconds
+        psize = 1024
+        pj = TiledJob(psize, args.precision, prefill=0, want_first=True)
+        if rank == 0:
+            cpu_first = oracle_first_eval(oracle_job(psize, full_net=False))
+            rec['parity_strips_vs_oracle'] = dict(parity_of(pj.first, cpu_first), canvas=[psize, psize], strips=world)
+        barrier()
+        pj.close()
+    else:
+        job.close()
+    return rec
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -199,30 +471,33 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('ST2_PRECISION', 'fp16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=25.0)
+    ap.add_argument('--canvas-size', type=int, default=4096)
+    ap.add_argument('--no-canvas', action='store_true', help='skip the config-4 record')
+    ap.add_argument('--no-sustained', action='store_true', help='skip the >= 3 s back-to-back section')
+    ap.add_argument('--sustained-seconds', type=float, default=3.0)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     canvas = args.workload == 'canvas'
-    size = args.size or (4096 if canvas else 1024)
+    size = args.size or (args.canvas_size if canvas else 1024)
     flops_conv = 2 * conv_flops(size, size)
     gram_flops = 0
-    dims = [(size, size)]
-    for _ in range(4):
-        dims.append((pool_extent(dims[-1][0]), pool_extent(dims[-1][1])))
+    dims = level_dims(size, size)
     for i, c in enumerate((64, 128, 256, 512, 512)):
         gram_flops += 4 * c * c * dims[i][0] * dims[i][1]
     config = {'workload': ('config4: one %dx%d canvas in row strips, ' if canvas else 'config2: %dx%d canvas, ') % (size, size) +
                           'style conv1_1..conv5_1 + content conv4_2, tv/p, L-BFGS m=10',
-              'canvas': [size, size], 'optimizer': 'lbfgs', 'precision': args.precision,
-              'parallelism': ('row strips x%d (halo rows over peer memory, 4 all-reduces/iteration)' % world) if canvas
+              'canvas': [size, size], 'optimizer': 'lbfgs',
+              'parallelism': ('row strips x%d (halo rows over peer memory, NCCL sum all-reduces)' % world) if canvas
                              else ('independent jobs x%d' % world if world > 1 else 'single job'),
               'l2': 'working set (>=1.3 GB activations + 0.25 GB L-BFGS history per iteration) exceeds the 126 MB L2',
+              'history_prefill_steps': HISTORY_PREFILL,
               'algorithmic_tflop_per_iteration': round((flops_conv + gram_flops) / 1e12, 4)}
 
     if args.impl == 'reference':
         if rank != 0:
             return
-        its, cores, sample, n = run_cpu_reference(size, args.steps, args.warmup, max(args.cpu_budget * 6, 60.0))
+        its, cores, sample, n, _ = run_cpu_reference(size, args.steps, args.warmup, max(args.cpu_budget * 6, 60.0))
         line = {'impl': 'reference', 'metric': 'style-transfer iterations/sec', 'value': its, 'unit': 'it/s',
                 'n_gpus': args.gpus, 'steps': n, 'warmup': max(args.warmup, 1), 'ms_per_step': 1000.0 / its,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -237,6 +512,8 @@ def main():
     import torch.distributed as dist
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
+    from style_transfer2_b200 import parallel
+    numa = parallel.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION; stdout carries the one JSON line
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
@@ -301,7 +578,7 @@ def main():
     if args.workload == 'serving':
         # BASELINE config 5: --jobs independent 512 x 512 jobs fed as message sequences to the job scheduler,
         # sharded over the ranks (job j -> rank j % world), --steps iterations each.
-        from style_transfer2_b200 import parallel, serving
+        from style_transfer2_b200 import serving
         from style_transfer2_b200.model import B200Model
         ssize = args.size or 512
         content, style, _ = load_images(ssize)
@@ -333,30 +610,21 @@ def main():
             dist.destroy_process_group()
         return
 
-    st = TiledJob(size, args.precision) if canvas else build_job(size, args.precision, seed_shift=rank)
+    peaks = load_peaks()
+    sampler = ClockSampler(local) if rank == 0 else None
+    want_parity = rank == 0 and world == 1 and not args.no_cpu_baseline and not canvas
+    if canvas:
+        st, gpu_first = TiledJob(size, args.precision), None
+    else:
+        st, gpu_first = build_job(size, args.precision, seed_shift=rank, want_first=want_parity)
     eng = st.engine
     jobs = 1 if canvas else world                 # whole-job units per step
+    warm = max(args.warmup, 3)
     # ---- device-resident arm: `value`
-    sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         st.step(fetch=False)
-    barrier()
-    l0 = eng.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        st.step(fetch=False)
-    e1.record()
-    barrier()
-    t1 = time.perf_counter()
-    ms = e0.elapsed_time(e1)
-    launches = eng.launches() - l0
-    clocks = sampler.stop(t0, t1) if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, launches, t0, t1 = timed_steps(st, args.steps, barrier, world, eng)
+    clocks = sampler.window(t0, t1) if sampler else None
     value = jobs * args.steps / (ms / 1000.0)
 
     # ---- end-to-end arm: the public step API with HOST buffers.  Every step uploads x from pinned host
@@ -408,61 +676,76 @@ def main():
     else:
         e2e = {'value': world * args.steps / (ms_e2e / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': nbytes,
                'd2h_bytes_per_step': 2 * nbytes + 8 * 560,
+               'pcie_gb_per_s_per_gpu': (3 * nbytes + 8 * 560) * args.steps / (ms_e2e / 1000.0) / 1e9,
+               'pinned_buffers_numa_node': numa,
                'note': 'StyleTransfer.step_async(): x uploaded from pinned host memory every step; new x + iterate image (HxWx3 fp32) + trace block read back every step, the image copy overlapping the next iteration'}
 
-    # ---- per-category device time (CUDA events on the launch stream) for the roofline
-    import ctypes as C
-    from style_transfer2_b200 import _lib
-    eng.call('st2_profile', 1)
-    prof_steps = min(args.steps, 10)
-    for _ in range(prof_steps):
-        st.step(fetch=False)
-    ms_cat = (C.c_double * _lib.PROF_CATS)()
-    n_cat = (C.c_longlong * _lib.PROF_CATS)()
-    eng.call('st2_profile_read', ms_cat, n_cat)
-    eng.call('st2_profile', 0)
-    cats = {name: {'ms_per_step': ms_cat[i] / prof_steps, 'launch_spans_per_step': n_cat[i] / prof_steps}
-            for i, name in enumerate(_lib.PROF_NAMES) if n_cat[i]}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    roofline = None
-    key = 'conv_tc' if 'conv_tc' in cats else ('conv_exact' if 'conv_exact' in cats else None)
-    if key:
-        fl = 2 * conv_flops(size, size, first=1) // (world if canvas else 1)   # conv1_2..conv5_1, fwd + dgrad, this GPU's share
-        t_s = cats[key]['ms_per_step'] / 1000.0
-        peak = peaks.get('bf16_tflops_sustained', 1400.0)
-        ach = fl / t_s / 1e12
-        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture of one
-        # iteration (profiles/*_tcconv_traffic.json, made by profiles/ncu_traffic.py); 1024^2 workload only
-        traffic, traffic_src = None, None
-        if key == 'conv_tc' and size == 1024 and not canvas:
-            import glob
-            found = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_tcconv_traffic.json')))
-            if found:
-                tj = json.load(open(found[-1]))
-                traffic, traffic_src = tj['conv3x3_dram_bytes_per_launch'], os.path.relpath(found[-1], ROOT)
-        n_launch = cats[key]['launch_spans_per_step']
-        roofline = {'kernel': 'tc_conv_kernel (tcgen05 implicit GEMM, fwd + dgrad, 24 launches/iteration)' if key == 'conv_tc' else 'conv_exact_kernel',
-                    'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                    'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
-                    'traffic_source': traffic_src, 'launches_per_step': n_launch,
-                    'flops_per_launch': fl / n_launch if n_launch else None,
-                    'avg_launch_ms': cats[key]['ms_per_step'] / n_launch if n_launch else None,
-                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s (of fallback)',
-                    'flops_per_step': fl, 'ms_per_step': cats[key]['ms_per_step']}
+    # ---- per-category device time (CUDA events on the launch stream) for the rooflines
+    cats = profile_categories(eng, lambda: st.step(fetch=False), min(args.steps, 10))
+    regime = regime_of(clocks)
+    roofline, rooflines = rooflines_of(cats, size, world if canvas else 1, peaks, regime, args.precision, canvas=canvas)
 
     line = {'metric': 'style-transfer iterations/sec', 'value': value, 'unit': 'it/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'steps': args.steps, 'warmup': warm, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'strong' if canvas else 'weak', 'vs_baseline': None,
             'dtype': 'f16 operands / f32 accumulate' if args.precision == 'fp16' else 'f32',
             'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
-            'roofline': roofline, 'kernel_time_ms_per_step': cats}
+            'roofline': roofline, 'rooflines': rooflines, 'kernel_time_ms_per_step': cats}
+
+    # ---- a true sustained figure: >= 3 s of back-to-back iterations with the clock sampled every 20 ms, then the
+    # per-category times again while the chip is still in that regime
+    if not args.no_sustained and not canvas:
+        per = max(ms / args.steps, 0.1)
+        n_sus = int(args.sustained_seconds * 1000.0 / per) + 1
+        ms_s, _, t0, t1 = timed_steps(st, n_sus, barrier, world, eng)
+        c_s = sampler.window(t0, t1) if sampler else None
+        cats_s = profile_categories(eng, lambda: st.step(fetch=False), 20)
+        r_s, _ = rooflines_of(cats_s, size, 1, peaks, regime_of(c_s), args.precision)
+        line['sustained'] = {'seconds': ms_s / 1000.0, 'steps': n_sus, 'value': jobs * n_sus / (ms_s / 1000.0), 'unit': 'it/s',
+                             'ms_per_step': ms_s / n_sus, 'clocks': c_s, 'roofline': r_s,
+                             'note': 'back-to-back iterations for >= %.0f s; category times taken from the 20 iterations right after' % args.sustained_seconds}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        its, cores, sample, _ = run_cpu_reference(size, 2, 1, args.cpu_budget)
+        its, cores, sample, _, cpu_first = run_cpu_reference(size, 6, 1, args.cpu_budget, first_eval=want_parity)
         line['cpu_baseline'] = {'value': its, 'unit': 'it/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        if want_parity and gpu_first is not None and cpu_first is not None:
+            line['parity'] = parity_of(gpu_first, cpu_first)
+
+    if world == 1 and not canvas and args.precision == 'fp16' and not args.no_sustained:
+        # the cost of exactness: the same job on the CUDA-core fp32 path (ST2_PREC_FP32), a few steps
+        try:
+            st32, _ = build_job(size, 'fp32', prefill=2)
+            ms32, _, _, _ = timed_steps(st32, 5, barrier, 1, st32.engine)
+            line['exact_fp32_path'] = {'value': 5 / (ms32 / 1000.0), 'unit': 'it/s', 'ms_per_step': ms32 / 5,
+                                       'note': 'CUDA-core fp32 convolutions (conv_exact_kernel), same job, 5 steps'}
+            st32.close()
+            del st32
+        except Exception as exc:          # auxiliary figure: never lose the line over it
+            line['exact_fp32_path'] = {'error': repr(exc)}
+
+    # ---- BASELINE config 4 at this N (skipped when it IS the headline workload)
+    if not canvas and not args.no_canvas:
+        if hasattr(st, 'close'):
+            st.close()
+        del st
+        torch.cuda.empty_cache()
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(240.0) and rank == 0:      # a wedged collective must not cost the whole line
+                line['canvas'] = {'error': 'config-4 section did not finish within 240 s'}
+                print(json.dumps(line), flush=True)
+                os._exit(0)
+            elif not done.is_set():
+                os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
+        try:
+            line['canvas'] = canvas_record(args, rank, world, local, sampler, peaks, barrier)
+        except Exception as exc:
+            line['canvas'] = {'error': repr(exc)}
+        done.set()
+    if sampler:
+        sampler.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

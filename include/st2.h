@@ -74,7 +74,8 @@ int st2_set_stream(st2_ctx* ctx, void* cuda_stream);
 long long st2_launch_count(st2_ctx* ctx);       /* kernels launched so far through this context */
 /* per-category device timing with CUDA events on the launch stream (off by default).  Categories:
  * 0 tcgen05 conv 3x3 (fwd+dgrad), 1 conv1_1 fwd/dgrad, 2 pool fwd/bwd, 3 Gram, 4 style gradient,
- * 5 loss reductions/combine, 6 pixel terms, 7 optimizer, 8 exact fp32 conv.
+ * 5 loss reductions/combine, 6 pixel terms, 7 optimizer, 8 exact fp32 conv, 9 halo exchange (row strips:
+ * peer stores + the wait for the neighbours' rows).
  * st2_profile_read SYNCHRONISES, writes elapsed milliseconds and span counts (ST2_PROF_CATS each)
  * accumulated since the last read, and clears them. */
 #define ST2_PROF_CATS 12
@@ -153,7 +154,7 @@ double* st2_scalars_dev(st2_plan* plan);
 /* ---- row strips: one canvas split over several GPUs (new; the reference holds the whole image in one
  * caffe.Net, worker.py:84-86, capped by max_size, app.py:183-185) --------------------------------
  * A strip plan holds rows [row0, row1) of an H_total x W canvas plus one halo row on either side of
- * every activation / gradient tensor.  Strips start at multiples of 16 rows.  x / grad / L-BFGS
+ * every activation / gradient tensor.  Strips start at multiples of 32 rows (all five pools stay strip-local).  x / grad / L-BFGS
  * vectors of a strip are dense fp32 (3, row1-row0, W).  Neighbouring strips (circular: the TV term
  * wraps around the canvas) are attached either through a CUDA IPC handle (one process per GPU; halo
  * rows then travel as peer stores over NVLink) or directly when they live in the same process.

@@ -54,6 +54,15 @@ struct st2_ctx {
   void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled entry point
   long long launches = 0;          // kernels launched through this context
   int debug_flags = 0;             // timing experiments only (st2_debug_flags)
+  // ST2_* environment knobs (kernel-selection experiments and the small-canvas tests that force the
+  // production kernels): read ONCE in st2_ctx_create, never on a launch path
+  struct Knobs {
+    bool no_fused_inject = false, no_tc_gram = false, no_tc_first = false, no_ws = false, force_pair = false,
+         wsp = false, no_pair = false, no_pool_fusion = false, no_style_fuse = false, no_graph = false;
+    int tc_bn = 0;
+    long long pair_min_tiles = -1;
+  } knobs;
+  double* dot_scratch = nullptr;   // st2_dot / st2_sumsq result slot (device)
   // optional per-category device timing (CUDA events on the launch stream), see st2_profile()
   bool prof_on = false;
   struct ProfSpan { int cat; cudaEvent_t a, b; };
@@ -79,6 +88,14 @@ struct St2KernelReg {
   St2KernelReg(std::initializer_list<const void*> fns) { for (const void* f : fns) st2_kernel_registry().push_back(f); }
 };
 #define ST2_KFN(...) reinterpret_cast<const void*>(&__VA_ARGS__)
+// Kernels that need more than 48 KB of dynamic shared memory: cudaFuncAttributeMaxDynamicSharedMemorySize is
+// per (function, device), so st2_ctx_create sets it for the context's device from this list (a process-wide
+// "already set" flag would leave a second device without the opt-in).
+struct St2SmemOptIn { const void* fn; int bytes; };
+std::vector<St2SmemOptIn>& st2_smem_registry();
+struct St2SmemReg {
+  St2SmemReg(std::initializer_list<St2SmemOptIn> fns) { for (const St2SmemOptIn& f : fns) st2_smem_registry().push_back(f); }
+};
 
 #define ST2_CUDA(ctx, expr)                                                             \
   do {                                                                                  \

@@ -272,11 +272,6 @@ int tc_first_pack_weights(st2_ctx* ctx, const float* w_oihw, __half* out) {
 
 int tc_first_fwd_launch(st2_ctx* ctx, TcFirstPlan* p, const float* x, long long xps, int lo, int hi, const __half* wpk,
                         const float* bias, __half* out) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_first_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF));
-    attr_set = true;
-  }
   const int H = p->g.H, W = p->g.W;
   if (p->out_base != (const void*)out) {
     cuuint64_t dims[3] = {64, (cuuint64_t)W, (cuuint64_t)H};
@@ -297,4 +292,5 @@ int tc_first_fwd_launch(st2_ctx* ctx, TcFirstPlan* p, const float* x, long long 
   return 0;
 }
 
+static St2SmemReg g_smem_first_tc({{ST2_KFN(tc_conv_first_fwd_kernel), kSmemF}});
 static St2KernelReg g_reg_first_tc({ST2_KFN(pack_x8_kernel), ST2_KFN(pack_w_first_kernel), ST2_KFN(tc_conv_first_fwd_kernel)});

@@ -1161,6 +1161,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace
 
+namespace {
+template <int BN> struct PairCfg {
+  static constexpr int KB = (BN == 256) ? 1 : 2;
+  static constexpr int kStages = (BN == 256) ? 6 : 4;
+  static constexpr int kSmemBytes = kStages * KB * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + 256;
+};
+template <int KB> struct WspCfg {
+  static constexpr int kStages = (KB == 1) ? 4 : 2;
+  static constexpr int kSmemBytes = KB * 9 * 64 * 128 + kStages * kPatchBytes + 1024 + 256;
+};
+}  // namespace
+
 struct TcConvPlan {
   CUtensorMap tmap_a, tmap_b;
   ConvGeom g;
@@ -1233,11 +1245,11 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
     const int kb[3] = {1, 2, 3};
     double best = 1e30;
     p->bn = 64;
-    const char* force = getenv("ST2_TC_BN");
+    const int force = ctx->knobs.tc_bn;
     for (int c = 0; c < 3; ++c) {
       const int bn = cand[c];
       if (cout % bn || first_bwd) continue;
-      if (force && atoi(force) == bn) { p->bn = bn; best = -1; break; }
+      if (force == bn) { p->bn = bn; best = -1; break; }
       const long long tiles = (long long)g.tiles_h * g.tiles_w * (cout / bn);
       const long long waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
       const double eff = bn == 256 ? 1.0 : (bn == 128 ? 1.30 : 1.8);   // shared-memory operand traffic per flop
@@ -1250,7 +1262,7 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   p->ws_kb = 0;
   // Only where N = 64: there the generic kernel starves on A-tile fill.  (Measured: with N = 128 the two
   // kernels tie -- conv2_1 fwd 54 vs 57 us, conv2_2 80 vs 78 us -- so those keep the generic path.)
-  if (first_bwd || (taps == 9 && cin <= 128 && cout == 64 && W >= 16 && H >= 16 && !getenv("ST2_NO_WS"))) {
+  if (first_bwd || (taps == 9 && cin <= 128 && cout == 64 && W >= 16 && H >= 16 && !ctx->knobs.no_ws)) {
     p->ws_kb = cin / 64;
     p->bn = first_bwd ? 16 : 64;                    // (64,1) (64,2) (16,1): weights + 2..4 patches fit in 227 KB
     g.TW = kWsTW; g.TH = kWsTH;
@@ -1258,14 +1270,14 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
     g.tiles_w = (W + g.TW - 1) / g.TW;
   }
   // ST2_FORCE_PAIR lets small test canvases reach the CTA-pair kernels (normally chosen by size)
-  const bool force_pair = getenv("ST2_FORCE_PAIR") != nullptr;
+  const bool force_pair = ctx->knobs.force_pair;
   // weight-stationary + CTA pair for the 128-channel layers (conv2_1 forward, conv2_2): N = 128, cin <= 128
   bool wsp = false;
   // OPT-IN (ST2_WSP=1): measured at 1024^2 after the epilogue stores were fixed, it wins only conv2_2 forward
   // (65.6 vs 71.3 us) and loses conv2_1 forward (55.8 vs 47.3) and conv2_2 data gradient (89.7 vs 82.4) to the
   // generic kernels -- with 2.4 us of MMA per tile the epilogue (one tile of look-ahead) is what bounds it.
-  if (!p->ws_kb && taps == 9 && cout == 128 && cin <= 128 && W >= 16 && H >= 32 && getenv("ST2_WSP") &&
-      !getenv("ST2_NO_PAIR")) {
+  if (!p->ws_kb && taps == 9 && cout == 128 && cin <= 128 && W >= 16 && H >= 32 && ctx->knobs.wsp &&
+      !ctx->knobs.no_pair) {
     const long long pair_tiles = (long long)((H + 31) / 32) * ((W + kWsTW - 1) / kWsTW);
     if (pair_tiles >= ctx->sm_count / 2 || force_pair) {
       wsp = true;
@@ -1282,12 +1294,12 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   p->pair = false;
   // (measured: N = 128 with a short K loop -- conv2_1 forward, 9 K blocks -- is faster on the single-CTA kernel)
   if (!p->ws_kb && taps == 9 && p->bn >= 128 && g.TW == 16 && (p->bn == 256 || taps * (cin / BK) >= 18) &&
-      !getenv("ST2_NO_PAIR")) {
+      !ctx->knobs.no_pair) {
     const long long pair_tiles = (long long)((H + 15) / 16) * g.tiles_w * g.n_blocks;
-    const char* min_env = getenv("ST2_PAIR_MIN_TILES");          // tuning experiments
+    const long long min_env = ctx->knobs.pair_min_tiles;          // tuning experiments
     // one full wave of pair tiles; N = 128 pays off from ~0.8 waves on (conv5_1 at 1024^2: 64 pair tiles on 74
     // pairs, 26.8 -> 22.7 us), N = 256 does not (31.6 vs 26.8 us there)
-    const long long min_tiles = min_env ? atoll(min_env) : (p->bn == 128 ? (ctx->sm_count * 2) / 5 : ctx->sm_count / 2);
+    const long long min_tiles = min_env >= 0 ? min_env : (p->bn == 128 ? (ctx->sm_count * 2) / 5 : ctx->sm_count / 2);
     if (pair_tiles >= min_tiles || force_pair) {
       p->pair = true;
       g.tiles_h = (H + 15) / 16;
@@ -1321,12 +1333,6 @@ void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
 template <int BN>
 static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                      float out_scale, double* sumsq, const TcInject& inj) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg<BN>::kSmemBytes));
-    attr_set = true;
-  }
   const int grid = p->g.total_tiles < ctx->sm_count ? p->g.total_tiles : ctx->sm_count;
   p->g.dbg = ctx->debug_flags;
   p->g.step_nb = grid % p->g.n_blocks;
@@ -1341,12 +1347,6 @@ static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
 template <int BN, int KB>
 static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                      const TcInject& inj) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_ws_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       WsCfg<BN, KB>::kSmemBytes));
-    attr_set = true;
-  }
   if (WsCfg<BN, KB>::kTmaStore && p->tmap_o_base != (const void*)out) {
     cuuint64_t dims[3] = {(cuuint64_t)p->g.cout, (cuuint64_t)p->g.W, (cuuint64_t)p->g.H};
     cuuint64_t strides[2] = {(cuuint64_t)p->g.cout * 2, (cuuint64_t)p->g.W * p->g.cout * 2};
@@ -1370,14 +1370,7 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
 template <int BN>
 static int launch_pair(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                        const TcInject& inj) {
-  constexpr int KB = (BN == 256) ? 1 : 2;
-  constexpr int kStages = (BN == 256) ? 6 : 4;
-  constexpr int smem = kStages * KB * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  constexpr int smem = PairCfg<BN>::kSmemBytes;
   int pairs = ctx->sm_count / 2;
   if (pairs > p->g.total_tiles) pairs = p->g.total_tiles;
   p->g.dbg = ctx->debug_flags;
@@ -1389,13 +1382,7 @@ static int launch_pair(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __h
 template <int KB>
 static int launch_wsp(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                       const TcInject& inj) {
-  constexpr int kStages = (KB == 1) ? 4 : 2;
-  constexpr int smem = KB * 9 * 64 * 128 + kStages * kPatchBytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_conv_wsp_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  constexpr int smem = WspCfg<KB>::kSmemBytes;
   const int nbk = p->g.n_blocks;
   const int n_pt = p->g.tiles_h * p->g.tiles_w;
   int per_nb = (ctx->sm_count / 2) / nbk;
@@ -1429,7 +1416,7 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     // the fused pool lives in the generic, CTA-pair and TMA-store weight-stationary epilogues
     const bool can_pool = epi == EPI_BIAS_RELU && inj.pool != nullptr && pooled != nullptr && out_scale == 1.f &&
                           sumsq == nullptr && !(p->ws_kb && p->pair) && !(p->ws_kb && !(p->ws_kb == 1 && p->bn == 64)) &&
-                          !getenv("ST2_NO_POOL_FUSION");
+                          !ctx->knobs.no_pool_fusion;
     if (!can_pool) { inj.pool = nullptr; inj.pool_wp = 0; }
     else *pooled = true;
   }
@@ -1451,6 +1438,13 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
   }
 }
 
+static St2SmemReg g_smem_conv_tc({
+    {ST2_KFN(tc_conv_kernel<256>), Cfg<256>::kSmemBytes}, {ST2_KFN(tc_conv_kernel<128>), Cfg<128>::kSmemBytes},
+    {ST2_KFN(tc_conv_kernel<64>), Cfg<64>::kSmemBytes},
+    {ST2_KFN(tc_conv_ws_kernel<64, 1>), WsCfg<64, 1>::kSmemBytes}, {ST2_KFN(tc_conv_ws_kernel<128, 1>), WsCfg<128, 1>::kSmemBytes},
+    {ST2_KFN(tc_conv_ws_kernel<64, 2>), WsCfg<64, 2>::kSmemBytes}, {ST2_KFN(tc_conv_ws_kernel<16, 1>), WsCfg<16, 1>::kSmemBytes},
+    {ST2_KFN(tc_conv2_kernel<256>), PairCfg<256>::kSmemBytes}, {ST2_KFN(tc_conv2_kernel<128>), PairCfg<128>::kSmemBytes},
+    {ST2_KFN(tc_conv_wsp_kernel<1>), WspCfg<1>::kSmemBytes}, {ST2_KFN(tc_conv_wsp_kernel<2>), WspCfg<2>::kSmemBytes}});
 static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>),
                                       ST2_KFN(tc_conv_ws_kernel<64, 1>), ST2_KFN(tc_conv_ws_kernel<128, 1>),
                                       ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>),

@@ -232,12 +232,6 @@ void tc_gram_plan_destroy(TcGramPlan* p) {
 
 template <int GN>
 static int launch_gn(st2_ctx* ctx, TcGramPlan* p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST2_CUDA(ctx, cudaFuncSetAttribute(tc_gram_kernel<GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       GCfg<GN>::kSmemBytes));
-    attr_set = true;
-  }
   dim3 grid(p->g.m_tiles * p->g.n_tiles, p->g.splits);
   tc_gram_kernel<GN><<<grid, kThreadsG, GCfg<GN>::kSmemBytes, ctx->stream>>>(p->tmap, p->g, p->partials);
   ST2_LAUNCH_CHECK(ctx);
@@ -275,5 +269,8 @@ int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double
   return 0;
 }
 
+static St2SmemReg g_smem_gram_tc({{ST2_KFN(tc_gram_kernel<256>), GCfg<256>::kSmemBytes},
+                                   {ST2_KFN(tc_gram_kernel<128>), GCfg<128>::kSmemBytes},
+                                   {ST2_KFN(tc_gram_kernel<64>), GCfg<64>::kSmemBytes}});
 static St2KernelReg g_reg_gram_tc({ST2_KFN(tc_gram_kernel<256>), ST2_KFN(tc_gram_kernel<128>), ST2_KFN(tc_gram_kernel<64>),
                                       ST2_KFN(gram_reduce_partials_kernel), ST2_KFN(gram_finalize_partials_kernel)});

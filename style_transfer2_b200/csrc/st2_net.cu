@@ -27,6 +27,11 @@ std::vector<const void*>& st2_kernel_registry() {
   return v;
 }
 
+std::vector<St2SmemOptIn>& st2_smem_registry() {
+  static std::vector<St2SmemOptIn> v;
+  return v;
+}
+
 int st2_fail(st2_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -410,6 +415,7 @@ static int halo_exchange(st2_plan* pl, int slot) {
       a.dst[side] = pbase + (side == 0 ? (size_t)(PL.rows[b] + 1) * rb : 0);
     }
   }
+  ProfScope ps(ctx, 9);
   long long vecs = a.seg_bytes / 16 * a.nseg;
   int blocks = (int)((vecs + 255) / 256);
   if (blocks < 1) blocks = 1;
@@ -528,7 +534,7 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
       } else if (pl->prec == ST2_PREC_FP32) {
         rc = launch_conv_exact(ctx, (const float*)cur.grad, ctx->wf32_bwd[ci], nullptr, (const float*)below.act,
                                (float*)below.grad, cur.H, cur.W, cur.C, below.C, mask_below ? EPI_MASK : EPI_RAW, lo, hi);
-      } else if (below_conv && inj[i - 1].on && inj[i - 1].coef != nullptr && !getenv("ST2_NO_FUSED_INJECT")) {
+      } else if (below_conv && inj[i - 1].on && inj[i - 1].coef != nullptr && !ctx->knobs.no_fused_inject) {
         TcInject ti;
         ti.fc = (const __half*)inj[i - 1].fc; ti.sraw = (const __half*)inj[i - 1].sraw; ti.coef = inj[i - 1].coef;
         ti.pool = nullptr; ti.pool_wp = 0;
@@ -562,7 +568,7 @@ static int gram_of_blob(st2_plan* pl, int blob, const float* A, float* D, double
   Blob& B = pl->b[blob];
   const long long HW = (long long)B.H * B.W;
   if (blob != 0 && pl->prec == ST2_PREC_FP16 && g_blobs[blob].kind == KIND_CONV && B.C % 64 == 0 &&
-      !getenv("ST2_NO_TC_GRAM")) {
+      !ctx->knobs.no_tc_gram) {
     if (!B.tc_gram) {
       int rc0 = tc_gram_plan_create(ctx, (const __half*)B.act, B.C, HW, &B.tc_gram);
       if (rc0) return rc0;
@@ -584,7 +590,7 @@ static int gram_sum_of_blob(st2_plan* pl, int blob, float* out) {
   Blob& B = pl->b[blob];
   const long long HW = (long long)B.H * B.W;
   if (blob != 0 && pl->prec == ST2_PREC_FP16 && g_blobs[blob].kind == KIND_CONV && B.C % 64 == 0 &&
-      !getenv("ST2_NO_TC_GRAM")) {
+      !ctx->knobs.no_tc_gram) {
     if (!B.tc_gram) {
       int rc0 = tc_gram_plan_create(ctx, (const __half*)B.act, B.C, HW, &B.tc_gram);
       if (rc0) return rc0;
@@ -800,9 +806,33 @@ int st2_ctx_create(int device, st2_ctx** out) {
     if ((e = cudaFuncGetAttributes(&attr, fn)) != cudaSuccess)
       return st2_fail(nullptr, ST2_ERR_CUDA, "loading the sm_100a kernels failed: %s", cudaGetErrorString(e));
   }
+  for (const St2SmemOptIn& k : st2_smem_registry()) {
+    if ((e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.bytes)) != cudaSuccess)
+      return st2_fail(nullptr, ST2_ERR_CUDA, "shared-memory opt-in (%d bytes) failed on device %d: %s", k.bytes, device,
+                      cudaGetErrorString(e));
+  }
   st2_ctx* ctx = new st2_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    st2_ctx::Knobs& k = ctx->knobs;
+    k.no_fused_inject = getenv("ST2_NO_FUSED_INJECT") != nullptr;
+    k.no_tc_gram = getenv("ST2_NO_TC_GRAM") != nullptr;
+    k.no_tc_first = getenv("ST2_NO_TC_FIRST") != nullptr;
+    k.no_ws = getenv("ST2_NO_WS") != nullptr;
+    k.force_pair = getenv("ST2_FORCE_PAIR") != nullptr;
+    k.wsp = getenv("ST2_WSP") != nullptr;
+    k.no_pair = getenv("ST2_NO_PAIR") != nullptr;
+    k.no_pool_fusion = getenv("ST2_NO_POOL_FUSION") != nullptr;
+    k.no_style_fuse = getenv("ST2_NO_STYLE_FUSE") != nullptr;
+    k.no_graph = getenv("ST2_NO_GRAPH") != nullptr;
+    if (const char* v = getenv("ST2_TC_BN")) k.tc_bn = atoi(v);
+    if (const char* v = getenv("ST2_PAIR_MIN_TILES")) k.pair_min_tiles = atoll(v);
+  }
+  if ((e = cudaMalloc(&ctx->dot_scratch, sizeof(double))) != cudaSuccess) {
+    delete ctx;
+    return st2_fail(nullptr, ST2_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+  }
   *out = ctx;
   return 0;
 }
@@ -814,6 +844,7 @@ void st2_ctx_destroy(st2_ctx* ctx) {
     cudaFree(ctx->wh_fwd[i]); cudaFree(ctx->wh_bwd[i]);
   }
   cudaFree(ctx->wh_first);
+  cudaFree(ctx->dot_scratch);
   delete ctx;
 }
 
@@ -937,7 +968,7 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
   ST2_CUDA(ctx, cudaMalloc(&pl->bwd, sizeof(float) * pl->b[0].n()));
   if (prec == ST2_PREC_FP16) {
     const int halo = strip ? 1 : 0;
-    if (ctx->wh_bwd[0] && pl->b[1].H >= 16 && pl->b[1].W >= 16 && !getenv("ST2_NO_TC_FIRST")) {
+    if (ctx->wh_bwd[0] && pl->b[1].H >= 16 && pl->b[1].W >= 16 && !ctx->knobs.no_tc_first) {
       Blob& c11 = pl->b[1];
       int rc = tc_conv_plan_create(ctx, (const __half*)(strip ? c11.grad_pad : c11.grad), ctx->wh_bwd[0], c11.H, c11.W, 64, 16,
                                    9, &c11.tc_bwd, halo);
@@ -973,9 +1004,10 @@ int st2_strip_plan_create(st2_ctx* ctx, int H_total, int W, int row0, int row1, 
   if (!ctx || !out || H_total < 1 || W < 1 || world < 1 || rank < 0 || rank >= world || row0 < 0 || row1 <= row0 ||
       row1 > H_total || (prec != ST2_PREC_FP32 && prec != ST2_PREC_FP16))
     return st2_fail(ctx, ST2_ERR_ARG, "st2_strip_plan_create: bad arguments");
-  // strips start on multiples of 16 rows so that all four 2x2/2 pools above a strip stay inside it
-  if (row0 % 16 || (rank != world - 1 && row1 % 16) || (rank == 0 && row0 != 0) || (rank == world - 1 && row1 != H_total))
-    return st2_fail(ctx, ST2_ERR_ARG, "st2_strip_plan_create: strip [%d, %d) of %d rows is not 16-row aligned", row0, row1,
+  // strips start on multiples of 32 rows so that all FIVE 2x2/2 pools (pool1 .. pool5) keep their windows inside
+  // a strip: the pool kernels are strip-local, a window straddling a boundary would be paired wrongly
+  if (row0 % 32 || (rank != world - 1 && row1 % 32) || (rank == 0 && row0 != 0) || (rank == world - 1 && row1 != H_total))
+    return st2_fail(ctx, ST2_ERR_ARG, "st2_strip_plan_create: strip [%d, %d) of %d rows is not 32-row aligned", row0, row1,
                     H_total);
   return plan_create_common(ctx, row1 - row0, W, prec, true, rank, world, row0, H_total, out);
 }

@@ -73,8 +73,7 @@ int st2_adam_step(st2_ctx* ctx, float* x, const float* g, float* m1, float* m2, 
 }
 
 static int reduce_to_host(st2_ctx* ctx, const float* a, const float* b, long long n, double* host_out) {
-  static double* scratch = nullptr;          // one double per process is enough (single stream)
-  if (!scratch) ST2_CUDA(ctx, cudaMalloc(&scratch, sizeof(double)));
+  double* scratch = ctx->dot_scratch;        // per context (= per device)
   ST2_CUDA(ctx, cudaMemsetAsync(scratch, 0, sizeof(double), ctx->stream));
   dot_kernel<<<grid_for(n, ctx->sm_count), kThreads, 0, ctx->stream>>>(a, b, n, scratch);
   ST2_LAUNCH_CHECK(ctx);

@@ -58,8 +58,8 @@ class AdamOptimizer:
         else:
             self.g1.mean = torch.zeros_like(self.x)
         if torch.is_tensor(self.g2.mean):
+            # max(0, .) (optimizers.py:39) is applied by the resampling kernel itself (clamp_min_zero)
             self.g2.mean = utils.resample_nchw(self.g2.mean, size, method=utils.BILINEAR, clamp_min_zero=True)
-            self.g2.mean.clamp_(min=0)
         return self.x
 
     def objective_changed(self):
@@ -131,6 +131,8 @@ class LBFGSOptimizer:
 
     # -- state access (teacher-forced parity tests, checkpointing)
     def export_state(self):
+        if self._h is None:                     # no x yet (the reference builds optimizers before any image is set)
+            return (torch.empty((0,)), torch.empty((0,)), [])
         cnt = C.c_int()
         S = torch.empty((self.n_corr, self._n), dtype=torch.float32, device=self.x.device)
         Y = torch.empty_like(S)
@@ -142,11 +144,16 @@ class LBFGSOptimizer:
 
     def load_state(self, S, Y, sy, grad, loss):
         """S, Y: (m, ...) arrays, oldest pair first; grad: gradient at the current x."""
+        self._ensure()
         dev = self.x.device
-        S = torch.as_tensor(np.ascontiguousarray(S, np.float32)).reshape(len(sy), -1).to(dev).contiguous()
-        Y = torch.as_tensor(np.ascontiguousarray(Y, np.float32)).reshape(len(sy), -1).to(dev).contiguous()
-        arr = (C.c_double * max(len(sy), 1))(*[float(v) for v in sy])
-        self._call('st2_lbfgs_load', len(sy), _p(S), _p(Y), arr)
+        m = len(sy)
+        arr = (C.c_double * max(m, 1))(*[float(v) for v in sy])
+        if m == 0:                              # e.g. a checkpoint taken right after objective_changed()
+            self._call('st2_lbfgs_load', 0, C.c_void_p(0), C.c_void_p(0), arr)
+        else:
+            S = torch.as_tensor(np.ascontiguousarray(S, np.float32)).reshape(m, -1).to(dev).contiguous()
+            Y = torch.as_tensor(np.ascontiguousarray(Y, np.float32)).reshape(m, -1).to(dev).contiguous()
+            self._call('st2_lbfgs_load', m, _p(S), _p(Y), arr)
         torch.cuda.synchronize(dev)
         self.grad = torch.as_tensor(np.ascontiguousarray(grad, np.float32)).to(dev).reshape(self.x.shape).contiguous()
         self.loss = loss

@@ -6,7 +6,7 @@ mirrors the part of ``worker.StyleTransfer`` (worker.py:117-315) that a job need
 ``set_input / set_content / set_style / set_weights / reset / opfunc / step`` -- for a canvas whose
 rows are partitioned over ``world`` strips:
 
-* every strip owns rows ``[row0, row1)`` (boundaries at multiples of 16 rows, ``parallel.strip_bounds``)
+* every strip owns rows ``[row0, row1)`` (boundaries at multiples of 32 rows, ``parallel.strip_bounds``)
   of x, of the gradient, of the L-BFGS history / Adam moments and of every activation;
 * before each 3x3 convolution (forward and data-gradient) the strips swap ONE boundary row.  libst2
   does that itself: a push kernel stores the row into the neighbour's halo row through peer memory
@@ -130,6 +130,10 @@ class TiledTransfer:
         self.H, self.W = int(height), int(width)
         self.dist = local_world is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if local_world is not None:
+            # every strip spins on its neighbours' flags from its own stream: more streams than hardware queues
+            # (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) could serialise a wait ahead of the push it waits for
+            if int(local_world) > 8:
+                raise ValueError('local_world is limited to 8 strips per process')
             self.world, ranks = int(local_world), list(range(int(local_world)))
         elif self.dist:
             self.world, ranks = dist.get_world_size(), [dist.get_rank()]
@@ -137,7 +141,7 @@ class TiledTransfer:
             self.world, ranks = 1, [0]
         bounds = parallel.strip_bounds(self.H, self.world)
         if any(e <= s for s, e in bounds):
-            raise ValueError('canvas of %d rows is too small for %d strips of >= 16 rows' % (self.H, self.world))
+            raise ValueError('canvas of %d rows is too small for %d strips of >= 32 rows' % (self.H, self.world))
         self.bounds = bounds
         dev = self.engine.device
         self.strips = []
@@ -200,6 +204,17 @@ class TiledTransfer:
         """Sum ``tensors[i]`` (one per local strip) over all strips, in place, stream-ordered."""
         if not tensors or tensors[0].numel() == 0:
             return
+        prof = getattr(self, 'allreduce_spans', None)      # bench.py: list of (start, end) events on strip 0's stream
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(self.strips[0].stream)
+        self._all_reduce(tensors)
+        if prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(self.strips[0].stream)
+            prof.append((e0, e1))
+
+    def _all_reduce(self, tensors):
         if len(self.strips) > 1:
             s0 = self.strips[0].stream
             for st in self.strips[1:]:
@@ -212,6 +227,9 @@ class TiledTransfer:
                 st.stream.wait_event(done)
                 with torch.cuda.stream(st.stream):
                     t.copy_(tensors[0])
+                # strip 0 goes on to overwrite its block (the next phase zeroes / refills it): not before every
+                # other strip has taken its copy
+                s0.wait_event(st.stream.record_event())
         if self.dist:
             with torch.cuda.stream(self.strips[0].stream):
                 dist.all_reduce(tensors[0])
@@ -440,20 +458,37 @@ class TiledTransfer:
         return self.image(), data
 
     # ------------------------------------------------------------------ results
-    def gather(self, per_strip):
-        """Full (1, 3, H, W) device tensor from per-local-strip row tensors (all ranks get it)."""
-        full = self.engine.zeros(1, 3, self.H, self.W)
+    def gather(self, per_strip, dst=0):
+        """Full (1, 3, H, W) device tensor from per-strip row tensors.  One process: assembled locally.  One
+        process per GPU: a gather to rank ``dst`` (every other rank sends its rows once and returns None)."""
         main = torch.cuda.current_stream(self.engine.device)
-        for st, t in zip(self.strips, per_strip):
+        for st in self.strips:
             main.wait_event(st.stream.record_event())
-            full[:, :, st.row0:st.row1, :] = t
-        if self.dist:
-            dist.all_reduce(full)
+        if not self.dist:
+            full = self.engine.empty(1, 3, self.H, self.W)
+            for st, t in zip(self.strips, per_strip):
+                full[:, :, st.row0:st.row1, :] = t
+            return full
+        me = self.strips[0]
+        mine = per_strip[0].contiguous()
+        if me.rank != dst:
+            dist.send(mine, dst)
+            return None
+        full = self.engine.empty(1, 3, self.H, self.W)
+        full[:, :, me.row0:me.row1, :] = mine
+        for r, (r0, r1) in enumerate(self.bounds):
+            if r == dst:
+                continue
+            part = self.engine.empty(1, 3, r1 - r0, self.W)
+            dist.recv(part, r)
+            full[:, :, r0:r1, :] = part
         return full
 
     def image(self):
         """Deprocessed iterate, HxWx3 fp32 host array (CaffeModel.deprocess, worker.py:68-71)."""
         x = self.gather([st.x for st in self.strips])
+        if x is None:                        # one process per GPU: rank 0 holds the iterate
+            return None
         hwc = self.engine.empty(self.H, self.W, 3)
         self.engine.sync_stream()
         self.engine.call('st2_deprocess', C.c_void_p(x.data_ptr()), C.c_void_p(hwc.data_ptr()), self.H, self.W)

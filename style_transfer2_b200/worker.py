@@ -41,7 +41,10 @@ def gram_matrix(x):
 class LazyTrace:
     """One evaluation's trace (utils.Trace, utils.py:257-282).  The scalar block is copied to pinned
     host memory asynchronously when the evaluation is enqueued; the dict is built (and the stream
-    event waited on) the first time ``data`` is read, so evaluations never stall the pipeline."""
+    event waited on) the first time ``data`` is read, so evaluations never stall the pipeline.
+    ``time`` is the host clock when the evaluation was ENQUEUED (the reference stamps it after its
+    synchronous evaluation, worker.py:298); differences between consecutive entries are still one
+    iteration each in steady state."""
 
     def __init__(self, host_block, event, spec, want_grad, when):
         self._host, self._event, self._spec = host_block, event, spec
@@ -245,7 +248,9 @@ class StyleTransfer:
         host = self._pinned_buffer((h, w, 3))
         host.copy_(hwc, non_blocking=True)
         torch.cuda.current_stream(self.engine.device).synchronize()
-        return host.numpy()
+        # a fresh array per iterate, as the reference returns (worker.py:68-71): callers may keep iterates across
+        # steps.  The pipelined path (step_async / IterateHandle) hands out the pinned double buffer itself.
+        return np.array(host.numpy())
 
     def image_async(self, x, trace):
         """Enqueue deprocess + device->host copy of ``x`` on the download stream; no host wait."""
@@ -530,6 +535,10 @@ class Worker:
                               base / config.get('caffemodel', 'models/vgg19.caffemodel'), gpu,
                               precision=config.get('precision', None))
         self.transfer = StyleTransfer(model)
+        # wire format of the iterates: the reference's send_pyobj pickles with the default protocol, so an app on
+        # an older Python can still read them; `pickle_protocol` in config.ini overrides (5 saves one 12.6 MB copy)
+        proto = config.get('pickle_protocol', None) if hasattr(config, 'get') else None
+        self.pickle_protocol = int(proto) if proto not in (None, '') else pickle.DEFAULT_PROTOCOL
         self.sock_out.send_pyobj(WorkerReady(layers=self.transfer.model.layers()))
 
     def run(self):
@@ -579,7 +588,7 @@ class Worker:
             # `image` is a view of a pinned double buffer: pickling copies it out right here, before the buffer can
             # be reused, so no intermediate np.array() copy; one frame, as recv_pyobj on the app side expects
             # (send_pyobj would pickle with the default protocol and then copy the 12.6 MB frame once more).
-            frame = pickle.dumps(Iterate(image, handle.t, dict(trace)), protocol=pickle.HIGHEST_PROTOCOL)
+            frame = pickle.dumps(Iterate(image, handle.t, dict(trace)), protocol=self.pickle_protocol)
             self.sock_out.send(frame, copy=False)
 
     def process_message(self, msg):

@@ -174,6 +174,6 @@ def test_strip_plan_rejects_misaligned_rows(models):
     from style_transfer2_b200.tiled import StripPlan
     m = models('fp32')
     with pytest.raises(_lib.St2Error):
-        StripPlan(m.engine, 64, 32, 8, 64, 1, 2, m.precision)        # strip must start on a multiple of 16 rows
+        StripPlan(m.engine, 64, 32, 8, 64, 1, 2, m.precision)        # strip must start on a multiple of 32 rows
     with pytest.raises(_lib.St2Error):
-        StripPlan(m.engine, 64, 32, 0, 24, 0, 2, m.precision)        # inner boundary not 16-aligned
+        StripPlan(m.engine, 64, 32, 0, 16, 0, 2, m.precision)        # inner boundary at an odd multiple of 16: splits a pool5 window

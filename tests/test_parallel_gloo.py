@@ -67,8 +67,23 @@ def test_strip_bounds_cover_canvas_and_align():
             b = parallel.strip_bounds(h, world)
             assert b[0][0] == 0 and len(b) == world
             assert all(s1 == e0 for (_, e0), (s1, _) in zip(b, b[1:]))
-            assert all(s % 16 == 0 for s, e in b if e > s)
+            assert all(s % 32 == 0 for s, e in b if e > s)
             assert max(e for _, e in b) == h
+
+
+def test_strip_bounds_keep_all_five_pools_strip_local():
+    """pool1..pool5 are 2x2/2 ceil-mode pools computed per strip: the strips' pooled row counts must add up to the
+    whole canvas' at every level (a boundary at an odd multiple of 16 rows would split a pool5 window: 1080 rows
+    over 8 strips gave 36 pool5 rows instead of 34)."""
+    from oracle.caffe_cpu import pool_out
+    for h in (4096, 3071, 1080, 1024, 150, 100):
+        for world in (1, 2, 4, 8):
+            b = [(s, e) for s, e in parallel.strip_bounds(h, world) if e > s]
+            whole, parts = h, [e - s for s, e in b]
+            for level in range(5):
+                whole = pool_out(whole)
+                parts = [pool_out(n) for n in parts]
+                assert sum(parts) == whole, (h, world, level)
 
 
 def test_single_process_fallbacks():

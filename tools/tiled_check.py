@@ -3,12 +3,13 @@
 under torchrun, halo rows over CUDA-IPC peer memory (NVLink), sums over NCCL.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29511 tools/tiled_check.py [--size 4096] [--steps 10] [--parity-size 256]
+        --master-port 29511 tools/tiled_check.py [--size 4096] [--steps 10] [--parity-size 256] [--oracle-size 1024]
 
 1. parity: a small canvas is evaluated tiled over the N GPUs and, on rank 0, un-split on one GPU; loss,
    every trace value and the gathered gradient must agree (fp32 2e-5, fp16 1e-3 / 2e-3), then 3 L-BFGS
    steps must stay >= 60 dB (fp32) from the un-split trajectory.
-2. timing: K L-BFGS iterations of the --size canvas, CUDA events, max over ranks.
+2. oracle parity: the --oracle-size canvas tiled over the N GPUs against the CPU ORACLE (loss / trace / gradient).
+3. timing: K L-BFGS iterations of the --size canvas, CUDA events, max over ranks.
 Rank 0 prints one JSON line per part.
 """
 import argparse
@@ -39,6 +40,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--parity-size', type=int, default=256)
     ap.add_argument('--precision', default='fp16')
+    ap.add_argument('--oracle-size', type=int, default=1024,
+                    help='canvas on which the strips are compared with the CPU ORACLE (0 = skip)')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -65,7 +68,8 @@ def main():
             tt.set_style(style)
             tt.set_weights(bench.WEIGHTS, bench.PARAMS)
             loss, grads = tt.opfunc()
-            grad = tt.gather(grads).cpu().numpy()
+            grad = tt.gather(grads)
+            grad = grad.cpu().numpy() if grad is not None else None
             tr = dict(tt.traces[-1].data)
             imgs = [tt.step()[0] for _ in range(3)]
             tt.check()
@@ -89,6 +93,21 @@ def main():
                 assert out['ok'], out
             tt.close()
             barrier()
+
+    # ---------------------------------------------------------------- strips vs the CPU oracle
+    if args.oracle_size:
+        model = B200Model(gpu=local, precision=args.precision)
+        pj = bench.TiledJob(args.oracle_size, args.precision, model=model, prefill=0, want_first=True)
+        pj.tt.check()
+        if rank == 0:
+            cpu_first = bench.oracle_first_eval(bench.oracle_job(args.oracle_size, full_net=False))
+            par = bench.parity_of(pj.first, cpu_first)
+            ok = par['loss_rel'] < 1e-3 and par['worst_loss_trace_rel'] < 1e-3 and par['grad_rel'] < 5e-2
+            print(json.dumps(dict(par, part='oracle_parity', precision=args.precision, world=world,
+                                  canvas=[args.oracle_size] * 2, ok=bool(ok))), flush=True)
+            assert ok, par
+        barrier()
+        pj.close()
 
     # ---------------------------------------------------------------- timing
     model = B200Model(gpu=local, precision=args.precision)
