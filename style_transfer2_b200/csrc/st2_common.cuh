@@ -148,6 +148,47 @@ __device__ __forceinline__ void block_accumulate(const float (&v)[NV], double* c
   }
 }
 
+// The same without contended atomics: every block stores its NV partial sums to part[blockIdx.x * NV ..], the last
+// block to finish (counter) adds them up in block order -- deterministic -- and does ONE add per destination.
+// `counter` must be 0 at launch and is left 0.  At most ST2_PART_BLOCKS blocks.
+#define ST2_PART_BLOCKS 1024
+template <int NV>
+__device__ __forceinline__ void block_accumulate_last(const float (&v)[NV], double* const (&dst)[NV], double* part,
+                                                      unsigned int* counter) {
+  __shared__ double sh[NV][32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double w = warp_sum_d((double)v[i]);
+    if (lane == 0) sh[i][warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double w = lane < nwarps ? sh[i][lane] : 0.0;
+      w = warp_sum_d(w);
+      if (lane == 0) part[(size_t)blockIdx.x * NV + i] = w;
+    }
+    if (lane == 0) {
+      __threadfence();
+      last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int i = warp; i < NV; i += nwarps) {
+    double w = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) w += __ldcg(part + (size_t)b * NV + i);
+    w = warp_sum_d(w);
+    if (lane == 0 && dst[i] != nullptr) *dst[i] += w;
+  }
+  if (threadIdx.x == 0) *counter = 0;
+}
+
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }

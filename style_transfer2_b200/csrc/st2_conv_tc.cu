@@ -828,9 +828,17 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (valid) {
           float* gx = reinterpret_cast<float*>(out);
           const long long plane = (long long)g.H * g.W, p = (long long)h * g.W + w;
-          gx[p] = __uint_as_float(r[0]);
-          gx[plane + p] = __uint_as_float(r[1]);
-          gx[2 * plane + p] = __uint_as_float(r[2]);
+          if (inj.coef != nullptr) {
+            // second pass over the same gradient planes: gx += coef[1] * acc (the style gradient of conv1_1 folded
+            // into this convolution's weights, see st2_net.cu style_fold_kernel)
+            gx[p] = fmaf(sc, __uint_as_float(r[0]), gx[p]);
+            gx[plane + p] = fmaf(sc, __uint_as_float(r[1]), gx[plane + p]);
+            gx[2 * plane + p] = fmaf(sc, __uint_as_float(r[2]), gx[2 * plane + p]);
+          } else {
+            gx[p] = __uint_as_float(r[0]);
+            gx[plane + p] = __uint_as_float(r[1]);
+            gx[2 * plane + p] = __uint_as_float(r[2]);
+          }
         }
         tc::fence_before_sync();
         __syncwarp();
@@ -1395,10 +1403,10 @@ static int launch_wsp(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __ha
   return 0;
 }
 
-int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx) {
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* accum_coef) {
   if (!p || p->bn != 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
   TcInject inj;
-  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr; inj.pool = nullptr; inj.pool_wp = 0;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = accum_coef; inj.pool = nullptr; inj.pool_wp = 0;
   return launch_ws<16, 1>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
 }
 

@@ -6,7 +6,9 @@
 // (SBO) and 64-channel groups 8 KB apart (LBO).  No transposed copy of F is ever made.
 // One CTA = one 128 x GN tile of G over one chunk of pixels (split-K across the whole GPU); fp32
 // accumulators live in TMEM; partial tiles go to a workspace with plain 128-byte row stores and are
-// summed (in double) by the finalize kernel -- deterministic, no atomics.
+// summed (in double) by ONE finalize launch for all style layers of an evaluation -- deterministic, no atomics.
+// (Measured, round 2: adding the partial tiles into a single accumulator with red.global.add.v4.f32 instead is 4x
+// SLOWER -- 16.8 M fp32 reductions per iteration run at ~20 per clock GPU-wide in the L2 atomic units.)
 #include "st2_kernels.h"
 #include "st2_tc.cuh"
 
@@ -141,51 +143,69 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramGeom g, float
   }
 }
 
-// D = (sum_s partial[s]) / (C*HW) - A ; sum D^2
-__global__ void gram_finalize_partials_kernel(const float* __restrict__ partials, int nsplit,
-                                              const float* __restrict__ A, float* __restrict__ D, int C,
-                                              long long HW, double* sum_dsq) {
-  const long long n = (long long)C * C;
-  const float denom = (float)((double)C * (double)HW);
-  float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    // four independent chains: the loop is latency-bound (up to 148 splits, one L2 round trip each)
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = 0;
-    for (; k + 4 <= nsplit; k += 4) {
-      s0 += (double)partials[(long long)k * n + i];
-      s1 += (double)partials[(long long)(k + 1) * n + i];
-      s2 += (double)partials[(long long)(k + 2) * n + i];
-      s3 += (double)partials[(long long)(k + 3) * n + i];
-    }
-    for (; k < nsplit; ++k) s0 += (double)partials[(long long)k * n + i];
-    const double s = (s0 + s1) + (s2 + s3);
-    float gv = (float)s / denom;
-    if (A != nullptr) gv -= A[i];
-    D[i] = gv;
-    acc = fmaf(gv, gv, acc);
-  }
-  float v[1] = {acc};
-  double* dst[1] = {sum_dsq};
-  block_accumulate<1>(v, dst);
-}
+// One launch finishes every Gram of an evaluation.  blockIdx.y = layer; a block = 8 split groups x 32 outputs:
+// thread (kg, o) sums the partials kg, kg + 8, ... of output o (two chains), the eight groups meet in shared memory,
+// so an output costs ~nsplit / 16 dependent L2 round trips instead of nsplit / 4 (the per-layer finalize of round 1
+// was pure latency: 10-13 us each, five launches).
+//   raw == 0:  D = (sum_s partial[s]) / (C*HW) - A ; *sum_dsq += sum D^2        raw == 1: D = sum_s partial[s]
+struct GramFinLayer {
+  const float* partials; const float* A; float* D; double* sum_dsq;
+  int nsplit, C; long long HW;
+};
+struct GramFinArgs { GramFinLayer l[8]; int raw; };
 
-// strip's un-normalised Gram sum: sum over the splits (in double), stored fp32
-__global__ void gram_reduce_partials_kernel(const float* __restrict__ partials, int nsplit,
-                                            float* __restrict__ out, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = 0;
-    for (; k + 4 <= nsplit; k += 4) {
-      s0 += (double)partials[(long long)k * n + i];
-      s1 += (double)partials[(long long)(k + 1) * n + i];
-      s2 += (double)partials[(long long)(k + 2) * n + i];
-      s3 += (double)partials[(long long)(k + 3) * n + i];
+__global__ void __launch_bounds__(256) gram_finalize_all_kernel(const GramFinArgs a) {
+  // 8 split groups x 32 lanes; a lane owns FOUR consecutive outputs (one 16-byte load per partial tile), and all of a
+  // thread's loads (<= 19 for 148 splits) are issued before the first add: the kernel streams 67 MB of partial tiles
+  // per iteration at 1024^2 and must keep that many bytes in flight, not chase one L2 round trip per split.
+  const GramFinLayer L = a.l[blockIdx.y];
+  __shared__ double sh[8][32][4];
+  const long long n = (long long)L.C * L.C;                  // multiple of 4096
+  const float denom = (float)((double)L.C * (double)L.HW);
+  const int kg = threadIdx.x >> 5, o = threadIdx.x & 31;
+  constexpr int kMaxPer = 19;                                // ceil(148 / 8)
+  float acc = 0.f;
+  for (long long base = (long long)blockIdx.x * 128; base < n; base += (long long)gridDim.x * 128) {
+    const long long i = base + 4 * o;
+    const float4* src = reinterpret_cast<const float4*>(L.partials + i);
+    const long long stride4 = n / 4;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = kg; k0 < L.nsplit; k0 += 8 * kMaxPer) {
+      float4 v[kMaxPer];
+#pragma unroll
+      for (int u = 0; u < kMaxPer; ++u) {
+        const int k = k0 + 8 * u;
+        v[u] = (k < L.nsplit) ? __ldcg(src + (long long)k * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kMaxPer; ++u) {
+        s[0] += (double)v[u].x; s[1] += (double)v[u].y; s[2] += (double)v[u].z; s[3] += (double)v[u].w;
+      }
     }
-    for (; k < nsplit; ++k) s0 += (double)partials[(long long)k * n + i];
-    out[i] = (float)((s0 + s1) + (s2 + s3));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sh[kg][o][e] = s[e];
+    __syncthreads();
+    if (kg < 4) {                                            // warp e finishes element e of every lane's quad
+      double t = 0.0;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) t += sh[g8][o][kg];
+      float gv = (float)t;
+      const long long ie = i + kg;
+      if (!a.raw) {
+        gv = gv / denom;
+        if (L.A != nullptr) gv -= L.A[ie];
+        acc = fmaf(gv, gv, acc);
+      }
+      L.D[ie] = gv;
+    }
+    __syncthreads();
+  }
+  if (!a.raw && L.sum_dsq != nullptr) {
+    __shared__ double wsum[8];
+    const double tot = warp_sum_d((double)acc);              // zero in warps 4..7
+    if (o == 0) wsum[kg] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(L.sum_dsq, (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]));
   }
 }
 
@@ -246,31 +266,37 @@ static int launch_mma(st2_ctx* ctx, TcGramPlan* p) {
   }
 }
 
+int tc_gram_mma_launch(st2_ctx* ctx, TcGramPlan* p) { return launch_mma(ctx, p); }
+
+int tc_gram_finalize_all(st2_ctx* ctx, int n, TcGramPlan* const* plans, const float* const* A, float* const* D,
+                         double* const* sum_dsq, int raw) {
+  if (n < 1 || n > 8) return st2_fail(ctx, ST2_ERR_ARG, "tc_gram_finalize_all: 1..8 layers");
+  GramFinArgs a;
+  a.raw = raw;
+  for (int i = 0; i < n; ++i) {
+    a.l[i].partials = plans[i]->partials; a.l[i].A = A ? A[i] : nullptr; a.l[i].D = D[i];
+    a.l[i].sum_dsq = sum_dsq ? sum_dsq[i] : nullptr;
+    a.l[i].nsplit = plans[i]->g.splits; a.l[i].C = plans[i]->g.C; a.l[i].HW = plans[i]->g.HW;
+  }
+  gram_finalize_all_kernel<<<dim3(ctx->sm_count, n), 256, 0, ctx->stream>>>(a);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 int tc_gram_sum_launch(st2_ctx* ctx, TcGramPlan* p, float* Gsum) {
   int rc = launch_mma(ctx, p);
   if (rc) return rc;
-  const long long n = (long long)p->g.C * p->g.C;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
-  gram_reduce_partials_kernel<<<blocks, 256, 0, ctx->stream>>>(p->partials, p->g.splits, Gsum, n);
-  ST2_LAUNCH_CHECK(ctx);
-  return 0;
+  return tc_gram_finalize_all(ctx, 1, &p, nullptr, &Gsum, nullptr, 1);
 }
 
 int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double* sum_dsq) {
   int rc = launch_mma(ctx, p);
   if (rc) return rc;
-  const long long n = (long long)p->g.C * p->g.C;
-  int blocks = (int)((n + 127) / 128);
-  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-  gram_finalize_partials_kernel<<<blocks, 128, 0, ctx->stream>>>(p->partials, p->g.splits, A, D, p->g.C, p->g.HW,
-                                                                 sum_dsq);
-  ST2_LAUNCH_CHECK(ctx);
-  return 0;
+  return tc_gram_finalize_all(ctx, 1, &p, &A, &D, &sum_dsq, 0);
 }
 
 static St2SmemReg g_smem_gram_tc({{ST2_KFN(tc_gram_kernel<256>), GCfg<256>::kSmemBytes},
                                    {ST2_KFN(tc_gram_kernel<128>), GCfg<128>::kSmemBytes},
                                    {ST2_KFN(tc_gram_kernel<64>), GCfg<64>::kSmemBytes}});
 static St2KernelReg g_reg_gram_tc({ST2_KFN(tc_gram_kernel<256>), ST2_KFN(tc_gram_kernel<128>), ST2_KFN(tc_gram_kernel<64>),
-                                      ST2_KFN(gram_reduce_partials_kernel), ST2_KFN(gram_finalize_partials_kernel)});
+                                      ST2_KFN(gram_finalize_all_kernel)});

@@ -67,7 +67,7 @@ int launch_add_inplace(st2_ctx* ctx, float* y, const float* x, float coef_host, 
 // of x are addressable halo rows) ------------------------------------------------------------------
 int pixel_terms_strip(st2_ctx* ctx, const float* x, long long xps, int wrap, const float* bwd, float* grad_out,
                       int C, int H, int W, float tv, float tv_power, float p, float p_power, float divisor,
-                      double* scal);
+                      double* scal, double* part = nullptr, unsigned int* counter = nullptr);
 
 // ---- st2_conv_tc.cu (tcgen05 implicit GEMM, fp16 NHWC) -----------------------------------------
 struct TcConvPlan;     // tensor maps + tile geometry for one (layer, direction, canvas)
@@ -86,7 +86,8 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
                    float out_scale, double* sumsq, const TcInject* inj = nullptr, bool* pooled = nullptr);
 // conv1_1 data gradient on the tensor cores: plan made with cin = 64, cout = 16 (the 3 image planes padded),
 // weights [16][tap'][64] fp16; writes fp32 NCHW (3 dense planes of H x W)
-int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx);
+// accum_coef != nullptr: gx += accum_coef[1] * conv (second pass with other weights over the same output planes)
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* accum_coef = nullptr);
 // ---- st2_conv_first_tc.cu: conv1_1 forward on the tensor cores (sliding-window K over pixel pairs) ---------
 struct TcFirstPlan;
 int tc_first_plan_create(st2_ctx* ctx, int H, int W, int halo_strip, TcFirstPlan** out);
@@ -103,6 +104,12 @@ void tc_gram_plan_destroy(TcGramPlan* p);
 int tc_gram_launch(st2_ctx* ctx, TcGramPlan* p, const float* A, float* D, double* sum_dsq);
 // row strips: Gsum (C x C fp32) = F^T F of this strip, un-normalised
 int tc_gram_sum_launch(st2_ctx* ctx, TcGramPlan* p, float* Gsum);
+// the two halves of the above, so that an evaluation finishes ALL its Grams with one launch: the split-K
+// contraction into the plan's partial tiles, then (raw = 0) D_i = sum / (C HW) - A_i and sum D_i^2, or (raw = 1)
+// D_i = sum, for n <= 8 plans at once
+int tc_gram_mma_launch(st2_ctx* ctx, TcGramPlan* p);
+int tc_gram_finalize_all(st2_ctx* ctx, int n, TcGramPlan* const* plans, const float* const* A, float* const* D,
+                         double* const* sum_dsq, int raw);
 
 // ---- st2_elementwise.cu: 16-byte-vectorised variants (fall back to the scalar kernels) ---------
 template <typename T> int launch_pool_fwd_v(st2_ctx* ctx, const T* in, T* out, int C, int H, int W);

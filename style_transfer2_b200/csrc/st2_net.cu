@@ -118,6 +118,48 @@ __global__ void style_scale_kernel(const float* __restrict__ D, __half* __restri
     Dh[i] = __float2half_rn(D[i] * ds);
 }
 
+// conv1_1 only.  Its style gradient s = sc (D F) enters blob.diff below the ReLU (worker.py:100) and goes straight
+// into conv1_1's own data-gradient convolution (worker.py:104), which is linear:
+//     gx += sc * convT_W(D F) = sc * convT_W'(F),     W'[plane][tap'][j] = sum_i W[plane][tap'][i] D[i][j].
+// So instead of materialising s (a 134 MB fp16 tensor at 1024^2, written by a 1x1 contraction and read back by
+// conv1_2's data-gradient epilogue) the 64 x 64 matrix D is folded into the 64 -> 3 weights once per evaluation and
+// the data-gradient kernel makes a second pass over F with W' (accumulating into the fp32 gradient planes).
+// The trace value and the normaliser need sum s^2, which needs no s either:
+//     sum_p |D' F_p|^2 = <D'^T D', F^T F> = <D'^T D', (D + A) C HW>      (D' = ds D, the scaled copy as before).
+// One block; D stays in L1.
+__global__ void __launch_bounds__(256)
+style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ w_oihw,
+                  __half* __restrict__ wfold, double n_total, double share, double* sb, double* raw_sum) {
+  constexpr int C = 64;
+  __shared__ double red[8];
+  const double rms = sqrt(sb[SB_S_GRAMSQ] / (double)(C * C));
+  float ds = 1.0f;
+  if (rms > 0.0 && isfinite(rms)) ds = exp2f(-ceilf(log2f((float)rms * (float)C)));
+  if (threadIdx.x == 0) sb[SB_S_DSCALE] = (double)ds;
+  for (int idx = threadIdx.x; idx < 3 * 9 * C; idx += blockDim.x) {
+    const int j = idx % C, tapf = (idx / C) % 9, plane = idx / (9 * C);
+    const int r = 2 - tapf / 3, sx = 2 - tapf % 3;              // tap' = flipped tap of the forward weights
+    float acc = 0.f;
+    for (int i = 0; i < C; ++i) acc = fmaf(w_oihw[((i * 3 + plane) * 3 + r) * 3 + sx], D[i * C + j], acc);
+    wfold[(plane * 9 + tapf) * C + j] = __float2half_rn(acc * ds);
+  }
+  double tot = 0.0;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int j = idx / C, k = idx % C;
+    double e = 0.0;
+    for (int i = 0; i < C; ++i) e += (double)D[i * C + j] * (double)D[i * C + k];
+    tot += e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0));
+  }
+  tot = warp_sum_d(tot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(raw_sum, t * (double)ds * (double)ds * n_total * share);
+  }
+}
+
 // worker.py:249-277: freeze normalisers on first use, derive combine coefficients and trace values
 __global__ void coef_kernel(EvalSpec es, double* scal) {
   const int k = threadIdx.x;
@@ -195,6 +237,8 @@ struct Blob {
   TcConvPlan* tc_fwd = nullptr;   // producing this blob (conv blobs, idx >= 1)
   TcConvPlan* tc_bwd = nullptr;   // consuming grad of this blob, producing grad of the blob below
   TcConvPlan* tc_style = nullptr;
+  TcConvPlan* tc_sfold = nullptr;  // conv1_1: second data-gradient pass over the activations with the folded weights
+  __half* wfold = nullptr;         // conv1_1: W' = W D (16 x 9 x 64 fp16, rows 3..15 zero)
   TcGramPlan* tc_gram = nullptr;
   TcFirstPlan* tc_first = nullptr; // conv1_1 only
   long long n() const { return (long long)C * H * W; }
@@ -203,6 +247,7 @@ struct Blob {
 
 struct Inject {
   bool on = false;
+  bool fold = false;          // conv1_1: the style term is applied by a second data-gradient pass (style_fold_kernel)
   const void* fc = nullptr;
   const void* sraw = nullptr;
   const double* coef = nullptr;
@@ -362,6 +407,8 @@ struct st2_plan {
   Blob b[ST2_NUM_BLOBS];
   double* scal = nullptr;
   double* gram_acc = nullptr;     // 512 x 512 doubles
+  double* part = nullptr;         // per-block partial sums of the reducing kernels (block_accumulate_last)
+  unsigned int* part_counter = nullptr;
   float* bwd = nullptr;           // d(scd)/d(data), fp32 NCHW
   float* data_sraw = nullptr;
   int order_n = 0;
@@ -529,6 +576,10 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
       const int ci = g_blobs[i].conv_index;
       if (ci == 0 && cur.tc_bwd) {
         rc = tc_conv_first_bwd_launch(ctx, cur.tc_bwd, grad_out);
+        if (!rc && inj[i].fold) {
+          ProfScope ps2(ctx, 4);
+          rc = tc_conv_first_bwd_launch(ctx, cur.tc_sfold, grad_out, inj[i].coef);
+        }
       } else if (ci == 0) {
         rc = launch_conv_first_bwd<T>(ctx, (const T*)cur.grad, ctx->wf32_bwd[0], grad_out, cur.H, cur.W, lo, hi);
       } else if (pl->prec == ST2_PREC_FP32) {
@@ -646,6 +697,9 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
 
   pl->gram_red_used = 0;
   for (int b = 0; b < ST2_NUM_BLOBS; ++b) pl->inj[b] = Inject();
+  // tensor-core Grams: the split-K contractions are launched per layer, ONE launch then finishes them all
+  TcGramPlan* gp[8]; const float* gA[8]; float* gD[8]; double* gS[8];
+  int n_gram = 0;
   for (int k = 0; k < es.n; ++k) {
     const int b = es.order[k];
     Blob& B = pl->b[b];
@@ -670,6 +724,19 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
       if (pl->strip) {
         pl->gram_red_off[b] = pl->gram_red_used;
         pl->gram_red_used += (long long)B.C * B.C;
+      }
+      const bool tc = b != 0 && pl->prec == ST2_PREC_FP16 && g_blobs[b].kind == KIND_CONV && B.C % 64 == 0 &&
+                      !ctx->knobs.no_tc_gram && n_gram < 8;
+      if (tc) {
+        if (!B.tc_gram && (rc = tc_gram_plan_create(ctx, (const __half*)B.act, B.C, (long long)B.H * B.W, &B.tc_gram)))
+          return rc;
+        if ((rc = tc_gram_mma_launch(ctx, B.tc_gram))) return rc;
+        gp[n_gram] = B.tc_gram;
+        gA[n_gram] = pl->strip ? nullptr : B.gram_target;
+        gD[n_gram] = pl->strip ? pl->gram_red + pl->gram_red_off[b] : B.D;
+        gS[n_gram] = pl->strip ? nullptr : sb + SB_S_GRAMSQ;
+        ++n_gram;
+      } else if (pl->strip) {
         if ((rc = gram_sum_of_blob<T>(pl, b, pl->gram_red + pl->gram_red_off[b]))) return rc;
       } else {
         if ((rc = gram_of_blob<T>(pl, b, B.gram_target, B.D, sb + SB_S_GRAMSQ))) return rc;
@@ -679,6 +746,10 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
     pl->inj[b].fc = c_on ? B.fc : nullptr;
     pl->inj[b].sraw = s_on ? B.sraw : nullptr;
     pl->inj[b].coef = sb + SB_C_COEF;          // [C_COEF, S_COEF, D_COEF] are consecutive
+  }
+  if (n_gram) {
+    ProfScope ps(ctx, 3);
+    if ((rc = tc_gram_finalize_all(ctx, n_gram, gp, gA, gD, gS, pl->strip ? 1 : 0))) return rc;
   }
   pl->eval_phase = 1;
   return 0;
@@ -705,6 +776,22 @@ static int eval_mid_impl(st2_plan* pl) {
         return rc;
     }
     ProfScope ps(ctx, 4);
+    if (b == 1 && B.tc_bwd != nullptr && pl->prec == ST2_PREC_FP16 && !ctx->knobs.no_style_fuse) {
+      if (!B.wfold) {
+        if ((rc = ensure(ctx, (void**)&B.wfold, sizeof(__half) * 16 * 9 * 64))) return rc;
+        ST2_CUDA(ctx, cudaMemsetAsync(B.wfold, 0, sizeof(__half) * 16 * 9 * 64, ctx->stream));
+      }
+      if (!B.tc_sfold && (rc = tc_conv_plan_create(ctx, (const __half*)(pl->strip ? B.act_pad : B.act), B.wfold, B.H, B.W, 64,
+                                                   16, 9, &B.tc_sfold, pl->strip ? 1 : 0)))
+        return rc;
+      // on strips every rank derives the same total from the all-reduced Gram: each contributes 1 / world of it
+      style_fold_kernel<<<1, 256, 0, ctx->stream>>>(B.D, B.gram_target, ctx->w_oihw[0], B.wfold, B.n_total(),
+                                                    1.0 / (double)pl->world, sb, raw_sum);
+      ST2_LAUNCH_CHECK(ctx);
+      pl->inj[b].sraw = nullptr;
+      pl->inj[b].fold = true;
+      continue;
+    }
     if (want_grad) {
       if (b == 0) {
         rc = launch_style_grad_generic<float>(ctx, (const float*)B.act, B.D, (float*)B.sraw, B.C, HW, 1, HW, raw_sum);
@@ -765,9 +852,10 @@ static int eval_end_impl(st2_plan* pl, float* grad_out) {
     ProfScope ps(ctx, 6);
     if (pl->strip)
       rc = pixel_terms_strip(ctx, pl->xp + pl->W, (long long)(pl->H + 2) * pl->W, 0, bwd, grad_out, 3, pl->H, pl->W,
-                             pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
+                             pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal, pl->part, pl->part_counter);
     else
-      rc = st2_pixel_terms(ctx, x, bwd, grad_out, 3, pl->H, pl->W, pl->tv, pl->tv_power, pl->p, pl->p_power, 255.0f, gscal);
+      rc = pixel_terms_strip(ctx, x, (long long)pl->H * pl->W, 1, bwd, grad_out, 3, pl->H, pl->W, pl->tv, pl->tv_power,
+                             pl->p, pl->p_power, 255.0f, gscal, pl->part, pl->part_counter);
   }
   if (rc) return rc;
   pl->eval_phase = 3;
@@ -965,6 +1053,9 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
   ST2_CUDA(ctx, cudaMalloc(&pl->scal, sizeof(double) * ST2_SCAL_TOTAL));
   ST2_CUDA(ctx, cudaMemsetAsync(pl->scal, 0, sizeof(double) * ST2_SCAL_TOTAL, ctx->stream));
   ST2_CUDA(ctx, cudaMalloc(&pl->gram_acc, sizeof(double) * 512 * 512));
+  ST2_CUDA(ctx, cudaMalloc(&pl->part, sizeof(double) * ST2_PART_BLOCKS * 8));
+  ST2_CUDA(ctx, cudaMalloc(&pl->part_counter, sizeof(unsigned int) * 4));
+  ST2_CUDA(ctx, cudaMemsetAsync(pl->part_counter, 0, sizeof(unsigned int) * 4, ctx->stream));
   ST2_CUDA(ctx, cudaMalloc(&pl->bwd, sizeof(float) * pl->b[0].n()));
   if (prec == ST2_PREC_FP16) {
     const int halo = strip ? 1 : 0;
@@ -1069,11 +1160,12 @@ void st2_plan_destroy(st2_plan* pl) {
     if (i > 0 && !pl->strip) { cudaFree(B.act); cudaFree(B.grad); }
     cudaFree(B.fc); cudaFree(B.sraw); cudaFree(B.inj); cudaFree(B.gram_target); cudaFree(B.D); cudaFree(B.Dh);
     tc_conv_plan_destroy(B.tc_fwd); tc_conv_plan_destroy(B.tc_bwd); tc_conv_plan_destroy(B.tc_style);
+    tc_conv_plan_destroy(B.tc_sfold); cudaFree(B.wfold);
     tc_gram_plan_destroy(B.tc_gram);
     tc_first_plan_destroy(B.tc_first);
   }
   cudaFree(pl->slab); cudaFree(pl->red); cudaFree(pl->gram_red);
-  cudaFree(pl->scal); cudaFree(pl->gram_acc); cudaFree(pl->bwd);
+  cudaFree(pl->scal); cudaFree(pl->gram_acc); cudaFree(pl->bwd); cudaFree(pl->part); cudaFree(pl->part_counter);
   delete pl;
 }
 
@@ -1296,5 +1388,5 @@ int st2_gram_nchw(st2_ctx* ctx, const float* x, int C, long long HW, float* out)
 }  // extern "C"
 
 static St2KernelReg g_reg_net({ST2_KFN(halo_exchange_kernel), ST2_KFN(pack_x_kernel),
-                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(scatter_sums_kernel),
+                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(style_fold_kernel), ST2_KFN(scatter_sums_kernel),
                                   ST2_KFN(coef_kernel), ST2_KFN(final_kernel), ST2_KFN(pack_weights_kernel)});

@@ -46,51 +46,88 @@ __device__ __forceinline__ float ipow(float m, int k) {
 //   grad = bwd + tv*tv_grad + p*p_grad
 constexpr int kPxRows = 8, kPxCols = 256;      // outputs per work item: 8 rows x 256 columns of one plane
 
+// TVM = 0: beta == 2 (k == 1, the reference's default tv_power: no pow at all); 1: general beta.
+// PI > 0: integer p known at compile time (p_power 6 is the stock value, 2 the other common one); 0: run-time p.
+// (ncu, round 2: the generic kernel issued ~156 instructions per output and stalled on instruction fetch; the
+// specialisations cut the arithmetic to what the stock parameters need.)
+template <int TVM, int PI>
 __global__ void __launch_bounds__(256)
 pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, float* __restrict__ grad, int C, int H,
                    int W, long long xps, int wrap, float tv, float beta, float pw, float pp, float divisor,
-                   double* scal) {
+                   double* scal, double* __restrict__ part, unsigned int* counter) {
   // x: row 0 of plane 0, planes xps floats apart.  wrap = 1: rows wrap around inside the tensor (whole
   // canvas); wrap = 0: rows -1 and H are addressable halo rows (a row strip; the strips at the canvas
   // edges hold the circular neighbours there).  bwd / grad are dense C x H x W.
   // Work item = 8 rows x 256 columns of one plane.  The (8 + 2) x (256 + 2) values v = x / 255 it needs are
   // divided ONCE (IEEE division, as the reference's x / 255) into shared memory; every output then reads its 7
-  // neighbours from there (the previous version divided 7 times per output and was bound by that).
+  // neighbours from there.  The staging loads are row-wise (thread = column, ten independent loads in flight per
+  // thread: the kernel is bound by load latency, ncu r1v: long-scoreboard stalls, 6.7 % DRAM), and so are the
+  // eight bwd loads of the compute phase, issued before the arithmetic.
+  // Sums: per-block partials -> `part` -> summed by the last block to finish (one writer per scalar instead of
+  // six same-line fp64 atomics per block); part == nullptr: plain atomics (stand-alone st2_pixel_terms).
   __shared__ float sv[kPxRows + 2][kPxCols + 2];
   const long long HW = (long long)H * W;
   const float half_beta = beta * 0.5f;
-  const int m_norm = (half_beta == 1.0f) ? 1 : 2;
+  const int m_norm = (TVM == 0 || half_beta == 1.0f) ? 1 : 2;
   const float e_k = half_beta - 1.0f;
-  const int m_k = (e_k == 0.0f) ? 0 : (e_k == 1.0f ? 1 : 2);
-  const int pi = (int)pp;
-  const bool p_int = ((float)pi == pp) && pi >= 1 && pi <= 16;
+  const int m_k = (TVM == 0 || e_k == 0.0f) ? 0 : (e_k == 1.0f ? 1 : 2);
+  const int pi = PI > 0 ? PI : (int)pp;
+  const bool p_int = PI > 0 || (((float)pi == pp) && pi >= 1 && pi <= 16);
   float s_tv = 0.f, s_p = 0.f, s_b = 0.f, s_t = 0.f, s_pg = 0.f, s_g = 0.f;
   const int bands = (H + kPxRows - 1) / kPxRows, chunks = (W + kPxCols - 1) / kPxCols;
   const int items = C * bands * chunks;
+  const int t = threadIdx.x;
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int ch = item % chunks, band = (item / chunks) % bands, c = item / (chunks * bands);
     const int h0 = band * kPxRows, w0 = ch * kPxCols;
     const float* xp = x + (long long)c * xps;
-    __syncthreads();
-    for (int i = threadIdx.x; i < (kPxRows + 2) * (kPxCols + 2); i += blockDim.x) {
-      const int r = i / (kPxCols + 2), q = i - r * (kPxCols + 2);
-      int hh = h0 + r - 1, ww = w0 + q - 1;
-      float v = 0.f;
-      if (hh <= H && ww <= W) {                 // beyond the canvas (ragged last band / chunk): unused
-        if (ww < 0) ww = W - 1; else if (ww == W) ww = 0;              // columns always wrap (utils.py:232-254)
-        if (wrap) { if (hh < 0) hh = H - 1; else if (hh == H) hh = 0; }
-        v = xp[(long long)hh * W + ww] / divisor;
+    const int w = w0 + t;
+    // bwd of this thread's eight outputs: independent of the staging, so in flight across the barrier
+    float bw[kPxRows];
+#pragma unroll
+    for (int r = 0; r < kPxRows; ++r) {
+      const int h = h0 + r;
+      bw[r] = (bwd != nullptr && grad != nullptr && h < H && w < W) ? __ldg(bwd + (long long)c * HW + (long long)h * W + w) : 0.f;
+    }
+    __syncthreads();                            // the previous item's readers are done with sv
+    {
+      // column q = t + 1 of every staged row (w0 + t), plus the two edge columns q = 0 and q = 257 by threads 0..19
+      int wc = w;                               // <= W: w == W is the wrap column of a ragged last chunk
+      if (wc == W) wc = 0;
+      float raw[kPxRows + 2];
+#pragma unroll
+      for (int r = 0; r < kPxRows + 2; ++r) {
+        int hh = h0 + r - 1;
+        float v = 0.f;
+        if (hh <= H && w <= W) {
+          if (wrap) { if (hh < 0) hh = H - 1; else if (hh == H) hh = 0; }
+          v = __ldg(xp + (long long)hh * W + wc);
+        }
+        raw[r] = v;
       }
-      sv[r][q] = v;
+      float edge = 0.f;
+      int er = 0, eq = 0;
+      if (t < 2 * (kPxRows + 2)) {
+        er = t >> 1;
+        eq = (t & 1) ? (kPxCols + 1) : 0;
+        int hh = h0 + er - 1, ww = w0 + eq - 1;
+        if (hh <= H && ww <= W) {
+          if (ww < 0) ww = W - 1; else if (ww == W) ww = 0;            // columns always wrap (utils.py:232-254)
+          if (wrap) { if (hh < 0) hh = H - 1; else if (hh == H) hh = 0; }
+          edge = __ldg(xp + (long long)hh * W + ww);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kPxRows + 2; ++r) sv[r][t + 1] = raw[r] / divisor;
+      if (t < 2 * (kPxRows + 2)) sv[er][eq] = edge / divisor;
     }
     __syncthreads();
-    const int w = w0 + threadIdx.x;
     if (w < W) {
 #pragma unroll
       for (int r = 0; r < kPxRows; ++r) {
         const int h = h0 + r;
         if (h >= H) break;
-        const int q = threadIdx.x + 1, rr = r + 1;
+        const int q = t + 1, rr = r + 1;
         const float v = sv[rr][q], vr = sv[rr][q + 1], vl = sv[rr][q - 1], vd = sv[rr + 1][q], vu = sv[rr - 1][q];
         const float vld = sv[rr + 1][q - 1], vur = sv[rr - 1][q + 1];
         // this pixel
@@ -111,7 +148,11 @@ pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, f
         s_tv += pow_beta(n0, half_beta, m_norm);
         const float mag = fabsf(v);
         float mp1;                                           // |v|^(p-1)
-        if (p_int) mp1 = ipow(mag, pi - 1); else mp1 = powf(mag, pp - 1.0f);
+        if (PI > 0) {
+          mp1 = 1.0f;
+#pragma unroll
+          for (int e = 0; e < PI - 1; ++e) mp1 *= mag;
+        } else if (p_int) mp1 = ipow(mag, pi - 1); else mp1 = powf(mag, pp - 1.0f);
         s_p += p_int ? mp1 * mag : powf(mag, pp);
         const float sgn = (v > 0.f) ? 1.f : (v < 0.f ? -1.f : 0.f);
         const float tgw = tv * tg;
@@ -120,7 +161,7 @@ pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, f
         s_pg = fmaf(pgw, pgw, s_pg);
         if (grad != nullptr) {
           const long long o = (long long)c * HW + (long long)h * W + w;
-          const float b = bwd ? bwd[o] : 0.f;
+          const float b = bw[r];
           float g = b + tgw;                                 // worker.py:295-297 order
           g += pgw;
           grad[o] = g;
@@ -133,7 +174,11 @@ pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, f
   float vals[6] = {s_tv, s_p, s_b, s_t, s_pg, s_g};
   double* dst[6] = {scal + ST2_G_TV_NORM, scal + ST2_G_P_NORM, scal + ST2_G_SCD_GRAD_SQ,
                     scal + ST2_G_T_GRAD_SQ, scal + ST2_G_P_GRAD_SQ, scal + ST2_G_GRAD_SQ};
-  block_accumulate<6>(vals, dst);
+  if (part == nullptr) {
+    block_accumulate<6>(vals, dst);
+    return;
+  }
+  block_accumulate_last<6>(vals, dst, part, counter);
 }
 
 // ---------------------------------------------------------------------------------- resampler
@@ -203,13 +248,20 @@ inline int ew_grid(long long n, int sm_count) {
 
 int pixel_terms_strip(st2_ctx* ctx, const float* x, long long xps, int wrap, const float* bwd, float* grad_out,
                       int C, int H, int W, float tv, float tv_power, float p, float p_power, float divisor,
-                      double* scal) {
+                      double* scal, double* part, unsigned int* counter) {
   if (!ctx || !x || !scal || C < 1 || H < 1 || W < 1) return st2_fail(ctx, ST2_ERR_ARG, "st2_pixel_terms: bad arguments");
-  // at most 6 blocks per SM: few blocks keep the 6 double atomics per block cheap
+  // whole waves of resident blocks (registers allow 5 per SM)
   int blocks = C * ((H + kPxRows - 1) / kPxRows) * ((W + kPxCols - 1) / kPxCols);
-  if (blocks > ctx->sm_count * 6) blocks = ctx->sm_count * 6;
-  pixel_terms_kernel<<<blocks, kThreads, 0, ctx->stream>>>(x, bwd, grad_out, C, H, W, xps, wrap, tv, tv_power, p, p_power,
-                                                           divisor, scal);
+  if (blocks > ctx->sm_count * 5) blocks = ctx->sm_count * 5;
+  if (blocks > ST2_PART_BLOCKS) blocks = ST2_PART_BLOCKS;
+#define ST2_PIXEL_LAUNCH(TVM, PI)                                                                                    \
+  pixel_terms_kernel<TVM, PI><<<blocks, kThreads, 0, ctx->stream>>>(x, bwd, grad_out, C, H, W, xps, wrap, tv, tv_power, p, \
+                                                                    p_power, divisor, scal, part, counter)
+  const bool b2 = tv_power == 2.0f;
+  if (p_power == 6.0f) { if (b2) ST2_PIXEL_LAUNCH(0, 6); else ST2_PIXEL_LAUNCH(1, 6); }
+  else if (p_power == 2.0f) { if (b2) ST2_PIXEL_LAUNCH(0, 2); else ST2_PIXEL_LAUNCH(1, 2); }
+  else { if (b2) ST2_PIXEL_LAUNCH(0, 0); else ST2_PIXEL_LAUNCH(1, 0); }
+#undef ST2_PIXEL_LAUNCH
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -218,7 +270,8 @@ extern "C" {
 
 int st2_pixel_terms(st2_ctx* ctx, const float* x, const float* bwd, float* grad_out, int C, int H, int W,
                     float tv, float tv_power, float p, float p_power, float divisor, double* scal) {
-  return pixel_terms_strip(ctx, x, (long long)H * W, 1, bwd, grad_out, C, H, W, tv, tv_power, p, p_power, divisor, scal);
+  return pixel_terms_strip(ctx, x, (long long)H * W, 1, bwd, grad_out, C, H, W, tv, tv_power, p, p_power, divisor, scal,
+                           nullptr, nullptr);
 }
 
 int st2_preprocess_u8(st2_ctx* ctx, const unsigned char* hwc, float* nchw, int h, int w) {
@@ -283,5 +336,7 @@ int st2_resample(st2_ctx* ctx, const float* src, int planes, int h_in, int w_in,
 
 }  // extern "C"
 
-static St2KernelReg g_reg_pixel({ST2_KFN(pixel_terms_kernel), ST2_KFN(preprocess_kernel<unsigned char>),
+static St2KernelReg g_reg_pixel({ST2_KFN(pixel_terms_kernel<0, 6>), ST2_KFN(pixel_terms_kernel<1, 6>),
+                                    ST2_KFN(pixel_terms_kernel<0, 2>), ST2_KFN(pixel_terms_kernel<1, 2>),
+                                    ST2_KFN(pixel_terms_kernel<0, 0>), ST2_KFN(pixel_terms_kernel<1, 0>), ST2_KFN(preprocess_kernel<unsigned char>),
                                     ST2_KFN(preprocess_kernel<float>), ST2_KFN(deprocess_kernel), ST2_KFN(resample_axis_kernel)});

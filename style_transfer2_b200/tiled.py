@@ -122,39 +122,43 @@ class _Strip:
         return self.row1 - self.row0
 
 
-class TiledTransfer:
-    """Row-tiled ``StyleTransfer``.  All ranks call every method in the same order (SPMD)."""
+class TiledIterate:
+    """An iterate of a tiled canvas on its way to the host (``TiledTransfer.step_async``): same surface as
+    ``worker.IterateHandle``.  Only the rank that assembles iterates (rank 0) gets an image; the others get None."""
 
-    def __init__(self, model, height, width, local_world=None, optimizer='lbfgs', step_size=None):
+    def __init__(self, host, done, trace, t, check):
+        self._host, self._done, self.trace, self.t, self._check = host, done, trace, t, check
+
+    def result(self):
+        data = self.trace.data                  # waits for this evaluation's scalar block
+        self._check(self.trace)
+        if self._host is None:
+            return None, data
+        self._done.synchronize()
+        return self._host.numpy(), data
+
+
+class TiledTransfer:
+    """Row-tiled ``StyleTransfer`` (worker.py:117-315): the same state machine and message-facing methods, for a
+    canvas whose rows are partitioned over ``world`` strips.  All ranks call every method in the same order (SPMD);
+    in a one-process-per-GPU worker rank 0 owns the sockets and every rank replays the same messages."""
+
+    def __init__(self, model, height=None, width=None, local_world=None, optimizer='lbfgs', step_size=None):
         self.model, self.engine = model, model.engine
-        self.H, self.W = int(height), int(width)
         self.dist = local_world is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if local_world is not None:
             # every strip spins on its neighbours' flags from its own stream: more streams than hardware queues
             # (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) could serialise a wait ahead of the push it waits for
             if int(local_world) > 8:
                 raise ValueError('local_world is limited to 8 strips per process')
-            self.world, ranks = int(local_world), list(range(int(local_world)))
+            self.world, self._ranks = int(local_world), list(range(int(local_world)))
         elif self.dist:
-            self.world, ranks = dist.get_world_size(), [dist.get_rank()]
+            self.world, self._ranks = dist.get_world_size(), [dist.get_rank()]
         else:
-            self.world, ranks = 1, [0]
-        bounds = parallel.strip_bounds(self.H, self.world)
-        if any(e <= s for s, e in bounds):
-            raise ValueError('canvas of %d rows is too small for %d strips of >= 32 rows' % (self.H, self.world))
-        self.bounds = bounds
-        dev = self.engine.device
-        self.strips = []
-        main = torch.cuda.current_stream(dev)
-        for r in ranks:
-            st = _Strip(r, *bounds[r])
-            st.stream = main if len(ranks) == 1 else torch.cuda.Stream(dev)
-            with torch.cuda.stream(st.stream):
-                self.engine.sync_stream()
-                st.plan = StripPlan(self.engine, self.H, self.W, st.row0, st.row1, r, self.world, model.precision)
-            self.strips.append(st)
-        torch.cuda.synchronize(dev)
-        self._attach()
+            self.world, self._ranks = 1, [0]
+        self.rank0 = self._ranks[0] == 0
+        self.H = self.W = None
+        self.bounds, self.strips = [], []
         self.weights = pd.DataFrame(np.ones((len(vgg.BLOBS), len(SetWeights.loss_names))), list(vgg.BLOBS),
                                     SetWeights.loss_names, np.float32)
         self.params = {w: 1 for w in SetWeights.scalar_loss_names}
@@ -164,15 +168,62 @@ class TiledTransfer:
         self.t = 0
         self.traces = []
         self.style = None
+        self.content = None            # the whole preprocessed content image (1, 3, Hc, Wc): strips slice it lazily
+        self.is_running = self.is_starting = False
+        self._have_opt = False         # an optimizer state exists (the reference's `self.optimizer is not None`)
         self._spec = []
         self._weights_dirty = True
         self._content_done, self._style_done = set(), set()
         self._have_eval = False
         self._cold = True
-        self._adam_items = 0
+        self._adam_items = self._adam_items2 = 0
+        self._pending_norms = {}
+        self._norm_source = None
+        self._dl = None
         self.loss = None
+        if height is not None:
+            self._layout(int(height), int(width))
 
     # ------------------------------------------------------------------ plumbing
+    def _layout(self, height, width):
+        """(Re)build the strips for a canvas size (the reference reshapes its net on demand, worker.py:84)."""
+        self._release_strips()
+        self.H, self.W = int(height), int(width)
+        bounds = parallel.strip_bounds(self.H, self.world)
+        if any(e <= s for s, e in bounds):
+            raise ValueError('canvas of %d rows is too small for %d strips of >= 32 rows' % (self.H, self.world))
+        self.bounds = bounds
+        dev = self.engine.device
+        main = torch.cuda.current_stream(dev)
+        for r in self._ranks:
+            st = _Strip(r, *bounds[r])
+            st.stream = main if len(self._ranks) == 1 else torch.cuda.Stream(dev)
+            with torch.cuda.stream(st.stream):
+                self.engine.sync_stream()
+                st.plan = StripPlan(self.engine, self.H, self.W, st.row0, st.row1, r, self.world, self.model.precision)
+            self.strips.append(st)
+        self.engine.sync_stream()
+        torch.cuda.synchronize(dev)
+        self._attach()
+        self._weights_dirty = True
+        self._content_done, self._style_done = set(), set()
+        self._have_eval = False
+        self._dl = None
+
+    def _release_strips(self):
+        if self.strips:
+            torch.cuda.synchronize(self.engine.device)
+            if self.dist:
+                dist.barrier()                   # nobody may still be pushing halo rows into a slab that is about to go
+        for st in self.strips:
+            if st.opt is not None:
+                self.engine.lib.st2_lbfgs_destroy(st.opt)
+                st.opt = None
+            if st.plan is not None:
+                st.plan.close()
+                st.plan = None
+        self.strips = []
+
     def _each(self):
         """Iterate the local strips with their stream current and libst2 pointed at it."""
         for st in self.strips:
@@ -238,6 +289,12 @@ class TiledTransfer:
         """Rows of a (1, 3, H, W) device tensor that belong to strip ``st`` (contiguous copy)."""
         return full[:, :, st.row0:st.row1, :].contiguous()
 
+    def _scatter(self, full, attr):
+        """Give every local strip its rows of a whole-canvas tensor (stored as ``strip.<attr>``)."""
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        for st in self._each():
+            setattr(st, attr, self._rows_of(full, st))
+
     def _upload(self, image):
         arr = np.asarray(image)
         h, w = arr.shape[:2]
@@ -246,33 +303,117 @@ class TiledTransfer:
         fn = 'st2_preprocess_u8' if arr.dtype == np.uint8 else 'st2_preprocess_f32'
         if arr.dtype != np.uint8:
             dev = dev.float().contiguous()
+        self.engine.sync_stream()
         self.engine.call(fn, C.c_void_p(dev.data_ptr()), C.c_void_p(out.data_ptr()), h, w)
         return out
 
-    # ------------------------------------------------------------------ job set-up (worker.py:191-229)
+    # ------------------------------------------------------------------ state machine (worker.py:140-189)
+    @property
+    def input_shape(self):
+        return None if self.H is None or not self.strips or self.strips[0].x is None else (1, 3, self.H, self.W)
+
+    @property
+    def grams(self):
+        return {'style': self.style} if self.style is not None else None
+
+    @property
+    def features(self):
+        return {'content': self.content} if self.content is not None else None
+
+    def check_consistency(self):
+        return bool(self.input_shape is not None and self.content is not None and self.grams
+                    and tuple(self.input_shape) == tuple(self.content.shape))
+
+    def pause(self):
+        self.is_running = False
+        self.is_starting = False
+
+    def start(self):
+        self.is_starting = True
+        self._start()
+        return self.is_running
+
+    def _start(self):
+        if self.is_starting and self.check_consistency():
+            if not self._have_opt:
+                self.reset()
+            self.is_starting = False
+            self.is_running = True
+
+    # ------------------------------------------------------------------ job set-up (worker.py:154-229)
     def set_input(self, image):
+        """worker.py:191-202."""
         full = self._upload(image)
-        if tuple(full.shape[2:]) != (self.H, self.W):
-            raise ValueError('input is %s, canvas is %s' % (tuple(full.shape[2:]), (self.H, self.W)))
-        torch.cuda.current_stream(self.engine.device).synchronize()
-        for st in self._each():
-            st.x = self._rows_of(full, st)
-        self.reset()
+        shape = tuple(full.shape[2:])
+        if self.input_shape is not None and shape == (self.H, self.W):
+            torch.cuda.current_stream(self.engine.device).synchronize()
+            for st in self._each():
+                st.x.copy_(full[:, :, st.row0:st.row1, :])
+            self.objective_changed()
+        elif self._have_opt:
+            self._adopt(full)                    # optimizer.resample(None, new_x=image)
+            self._start()
+        else:
+            if (self.H, self.W) != shape or not self.strips:
+                self._relayout(*shape)
+            self._scatter(full, 'x')
+            self.reset()
+            self._start()
 
     def set_content(self, image):
-        full = self._upload(image)
-        if tuple(full.shape[2:]) != (self.H, self.W):
-            raise ValueError('content is %s, canvas is %s' % (tuple(full.shape[2:]), (self.H, self.W)))
-        torch.cuda.current_stream(self.engine.device).synchronize()
-        for st in self._each():
-            st.content = self._rows_of(full, st)
+        """worker.py:204-209.  The whole content image is kept; strips take their rows when the canvas matches."""
+        self.content = self._upload(image)
         self._content_done = set()
+        self._start()
         self.objective_changed()
 
     def set_style(self, image):
         self.style = self._upload(image)
         self._style_done = set()
+        self._start()
         self.objective_changed()
+
+    def resample_input(self, size):
+        """worker.py:154-160."""
+        size = tuple(int(v) for v in size)
+        if self.input_shape is not None and self._have_opt:
+            self._adopt(None, size)
+        else:
+            self._relayout(*size)
+            self._scatter(self.engine.zeros(1, 3, *size), 'x')
+        self._start()
+        self.objective_changed()
+
+    def resample_content(self, size):
+        """worker.py:162-170."""
+        size = tuple(int(v) for v in size)
+        utils.set_default_engine(self.engine)
+        self.engine.sync_stream()
+        if self.content is not None:
+            self.content = utils.resample_nchw(self.content, size)
+        else:
+            self.content = self.engine.zeros(1, 3, *size)
+        self._content_done = set()
+        self._start()
+        self.objective_changed()
+
+    def set_step_size(self, step_size):
+        self.step_size = step_size
+
+    def set_optimizer_class(self, cls, step_size):
+        """worker.py:387-391 (SetOptimizer): switch class / step size; a class change resets the job state."""
+        name = 'adam' if cls is optimizers.AdamOptimizer or getattr(cls, '__name__', '') == 'AdamOptimizer' else 'lbfgs'
+        self.set_step_size(step_size)
+        if name != self.optimizer_name:
+            self.optimizer_name = name
+            if self.input_shape is not None:
+                self.reset()
+            else:
+                self._have_opt = False
+
+    @property
+    def optimizer_cls(self):
+        return optimizers.AdamOptimizer if self.optimizer_name == 'adam' else optimizers.LBFGSOptimizer
 
     def set_weights(self, weights, params):
         self.weights = pd.DataFrame.from_dict(weights, dtype=np.float32)
@@ -295,13 +436,13 @@ class TiledTransfer:
                 if st.m1 is not None:
                     st.m1.zero_()
 
-    def reset(self):
-        """worker.py:172-175: new norms, t = 0, fresh optimizer state."""
+    def _new_optimizer_state(self):
         for st in self._each():
-            st.plan.reset_norms()
+            if st.opt is not None:
+                self.engine.lib.st2_lbfgs_destroy(st.opt)
+                st.opt = None
+            st.m1 = st.m2 = None
             if self.optimizer_name == 'lbfgs':
-                if st.opt is not None:
-                    self.engine.lib.st2_lbfgs_destroy(st.opt)
                 h = C.c_void_p()
                 self.engine.call('st2_lbfgs_create', st.x.numel(), 10, C.byref(h))
                 _lib.check(self.engine.ctx, self.engine.lib.st2_lbfgs_set_global_length(h, float(3 * self.H * self.W)),
@@ -311,9 +452,79 @@ class TiledTransfer:
                 st.m1 = torch.zeros_like(st.x)
                 st.m2 = torch.zeros_like(st.x)
         self._cold = True
+        self._have_eval = False
+        self._have_opt = True
+
+    def reset(self):
+        """worker.py:172-175: new norms, t = 0, fresh optimizer state."""
+        for st in self._each():
+            st.plan.reset_norms()
+        self._pending_norms = {}
+        self._norm_source = None
+        self._new_optimizer_state()
         self._adam_items = self._adam_items2 = 0
         self.t = 0
-        self._have_eval = False
+
+    # ------------------------------------------------------------------ scale changes (cold path)
+    def _whole(self, attr):
+        """The whole-canvas tensor assembled from ``strip.<attr>`` on EVERY rank (cold path: scale changes)."""
+        main = torch.cuda.current_stream(self.engine.device)
+        full = self.engine.zeros(1, 3, self.H, self.W)
+        for st in self.strips:
+            main.wait_event(st.stream.record_event())
+            full[:, :, st.row0:st.row1, :] = getattr(st, attr)
+        if self.dist:
+            dist.all_reduce(full)            # zero-filled sum = all-gather of ragged strips; cold path only
+        return full
+
+    def _relayout(self, height, width):
+        """New strips for a new canvas size; frozen normalisers survive the change (they are job state, worker.py:172)."""
+        if self._norm_source is not None:
+            for kind, table in self.norms.items():
+                for layer, v in table.items():
+                    self._pending_norms.setdefault((kind, layer), v)
+        self._norm_source = None
+        self._layout(height, width)
+
+    def _adopt(self, new_x, size=None):
+        """``optimizer.resample(size, new_x)`` (optimizers.py:29-40, 110-119) on sharded state: x is replaced by
+        ``new_x`` or Lanczos-resampled; Adam's first moment Lanczos, second moment bilinear then max(0, .);
+        L-BFGS drops its history."""
+        utils.set_default_engine(self.engine)
+        self.engine.sync_stream()
+        adam = self.optimizer_name == 'adam'
+        m1 = m2 = None
+        if new_x is None:
+            new_x = utils.resample_nchw(self._whole('x'), size)
+        else:
+            size = tuple(new_x.shape[2:])
+        if adam:
+            m2 = utils.resample_nchw(self._whole('m2'), size, method=utils.BILINEAR, clamp_min_zero=True)
+            m1 = utils.resample_nchw(self._whole('m1'), size) if self._adam_items else None
+        items = (self._adam_items, self._adam_items2)
+        self._relayout(*size)
+        self._scatter(new_x, 'x')
+        self._new_optimizer_state()
+        if adam:
+            self._scatter(m2, 'm2')
+            if m1 is not None:
+                self._scatter(m1, 'm1')
+            self._adam_items, self._adam_items2 = items
+        else:
+            self.objective_changed()
+
+    # ------------------------------------------------------------------ norms (checkpointing, scale changes)
+    @property
+    def norms(self):
+        out = self._norm_source.norms() if self._norm_source is not None else {k: {} for k in 'cds'}
+        for (kind, layer), v in self._pending_norms.items():
+            out[kind][layer] = v
+        return out
+
+    def set_norms(self, norms):
+        for kind, table in norms.items():
+            for layer, v in table.items():
+                self._pending_norms[(kind, layer)] = float(v)
 
     def active_layers(self):
         nonzeros = abs(self.weights) > EPS_W
@@ -325,6 +536,8 @@ class TiledTransfer:
             table = self.weights
             rows = []
             for name in self.active_layers():
+                if name not in vgg.BLOB_INDEX:
+                    raise KeyError('unknown layer %r' % name)
                 b = vgg.BLOB_INDEX[name]
                 vals = [float(table[col][name]) if col in table.columns else 0.0 for col in SetWeights.loss_names]
                 vals = [0.0 if (np.isnan(v) or abs(v) <= EPS_W) else v for v in vals]
@@ -341,9 +554,18 @@ class TiledTransfer:
                                    float(self.params['p_power']))
             self._spec = spec
             self._weights_dirty = False
+        if self._pending_norms:
+            for st in self._each():
+                for (kind, layer), v in self._pending_norms.items():
+                    st.plan.set_norm(kind, vgg.BLOB_INDEX[layer], v)
+            self._pending_norms = {}
         need_c = [b for b, c_on, _, _ in self._spec if c_on and b not in self._content_done]
         if need_c:
+            if tuple(self.content.shape[2:]) != (self.H, self.W):
+                raise RuntimeError('content is %s, canvas is %s' % (tuple(self.content.shape[2:]), (self.H, self.W)))
+            torch.cuda.current_stream(self.engine.device).synchronize()
             for st in self._each():
+                st.content = self._rows_of(self.content, st)
                 st.plan.forward(st.content, max(need_c))
                 for b in need_c:
                     st.plan.capture_content(b)
@@ -373,7 +595,7 @@ class TiledTransfer:
         for st in self._each():
             if return_grad:
                 st.turn ^= 1
-                if st.grads[st.turn] is None:
+                if st.grads[st.turn] is None or st.grads[st.turn].shape != st.x.shape:
                     st.grads[st.turn] = torch.empty_like(st.x)
                 grads.append(st.grads[st.turn])
             st.plan.eval_begin(st.x, return_grad)
@@ -397,6 +619,7 @@ class TiledTransfer:
         self.engine.sync_stream()
         tr.halo_timeout = lambda tr=tr: bool(tr._host[_lib.SCAL_GLOBAL_BASE + _lib.G_HALO_TIMEOUT] != 0.0)
         self.traces.append(tr)
+        self._norm_source = tr
         del self.traces[:-256]
         return (LazyLoss(tr), grads) if return_grad else LazyLoss(tr)
 
@@ -437,25 +660,65 @@ class TiledTransfer:
         """optimizers.py:20-27: purely element-wise, no reduction."""
         loss, grads = self.opfunc()
         self._adam_items += 1
-        self._adam_items2 = getattr(self, '_adam_items2', 0) + 1
+        self._adam_items2 += 1
         for st, g in zip(self._each(), grads):
             self.engine.call('st2_adam_step', _ptr(st.x), _ptr(g), _ptr(st.m1), _ptr(st.m2), st.x.numel(),
                              float(self.step_size), self.b1, self.b2, self._adam_items, self._adam_items2)
         self.loss = loss
         return loss
 
-    def step(self, fetch=True):
-        """worker.py:303-310."""
+    def _advance(self):
+        if not self._have_opt:
+            self.reset()
         self.t += 1
         loss = self._step_lbfgs() if self.optimizer_name == 'lbfgs' else self._step_adam()
         tr = self.traces[-1]
         tr('fevals', self.t)
+        return tr
+
+    def _raise_on_halo_timeout(self, tr):
+        if tr.halo_timeout():
+            raise RuntimeError('a halo exchange timed out: a neighbouring strip stopped (rank %d)' % self.strips[0].rank)
+
+    def step(self, fetch=True):
+        """worker.py:303-310."""
+        tr = self._advance()
         if not fetch:
             return None, None
         data = tr.data                       # waits for this evaluation's scalar block
-        if tr.halo_timeout():
-            raise RuntimeError('a halo exchange timed out: a neighbouring strip stopped (rank %d)' % self.strips[0].rank)
+        self._raise_on_halo_timeout(tr)
         return self.image(), data
+
+    def step_async(self):
+        """``step()`` without the host wait (worker.StyleTransfer.step_async): the iterate is assembled on rank 0,
+        deprocessed and copied to a pinned double buffer on a side stream while the next iteration computes."""
+        tr = self._advance()
+        dev = self.engine.device
+        main = torch.cuda.current_stream(dev)
+        x = self.gather([st.x for st in self.strips])
+        if x is None:
+            return TiledIterate(None, None, tr, self.t, self._raise_on_halo_timeout)
+        if self._dl is None or self._dl['shape'] != (self.H, self.W):
+            self._dl = {'shape': (self.H, self.W), 'stream': torch.cuda.Stream(dev), 'turn': 0,
+                        'dev': [self.engine.empty(self.H, self.W, 3) for _ in range(2)],
+                        'host': [torch.empty((self.H, self.W, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)],
+                        'done': [None, None]}
+        d = self._dl
+        d['turn'] ^= 1
+        k = d['turn']
+        if d['done'][k] is not None:
+            main.wait_event(d['done'][k])
+        self.engine.sync_stream()
+        self.engine.call('st2_deprocess', C.c_void_p(x.data_ptr()), C.c_void_p(d['dev'][k].data_ptr()), self.H, self.W)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(d['stream']):
+            d['stream'].wait_event(ready)
+            d['host'][k].copy_(d['dev'][k], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(d['stream'])
+        d['done'][k] = done
+        return TiledIterate(d['host'][k], done, tr, self.t, self._raise_on_halo_timeout)
 
     # ------------------------------------------------------------------ results
     def gather(self, per_strip, dst=0):
@@ -501,10 +764,4 @@ class TiledTransfer:
                 raise RuntimeError('strip %d: halo exchange timed out' % st.rank)
 
     def close(self):
-        for st in self.strips:
-            if st.opt is not None:
-                self.engine.lib.st2_lbfgs_destroy(st.opt)
-                st.opt = None
-            if st.plan is not None:
-                st.plan.close()
-                st.plan = None
+        self._release_strips()

@@ -11,6 +11,7 @@ from collections import OrderedDict
 import ctypes as C
 import logging
 import math
+import os
 import pickle
 import sys
 import time
@@ -232,7 +233,7 @@ class StyleTransfer:
         h, w = arr.shape[:2]
         out = self.engine.empty(1, 3, h, w)
         if arr.dtype == np.uint8:
-            dev = torch.from_numpy(np.ascontiguousarray(arr)).to(self.engine.device)
+            dev = torch.from_numpy(np.array(arr, copy=True)).to(self.engine.device)     # (messages may hold read-only arrays)
             self.engine.call('st2_preprocess_u8', C.c_void_p(dev.data_ptr()), C.c_void_p(out.data_ptr()), h, w)
         else:
             dev = torch.from_numpy(np.ascontiguousarray(arr, np.float32)).to(self.engine.device)
@@ -374,6 +375,13 @@ class StyleTransfer:
         self.step_size = step_size
         if self.optimizer is not None:
             self.optimizer.step_size = step_size
+
+    def set_optimizer_class(self, cls, step_size):
+        """worker.py:387-391 (SetOptimizer): switch class / step size; a class change resets the job state."""
+        self.optimizer_cls = cls
+        self.set_step_size(step_size)
+        if not isinstance(self.optimizer, self.optimizer_cls):
+            self.reset()
 
     def set_weights(self, weights, params):
         """worker.py:226-229."""
@@ -517,59 +525,103 @@ class StyleTransfer:
 
 class Worker:
     """worker.py:318-409: bind PULL on ``worker_socket``, connect PUSH to ``app_socket``, announce
-    ``WorkerReady``, then drain-all-messages-then-one-step until ``Shutdown``."""
+    ``WorkerReady``, then drain-all-messages-then-one-step until ``Shutdown``.
+
+    Two optional ``config.ini`` keys put the tiling scheduler (``tiled.TiledTransfer``, BASELINE config 4) behind
+    the same protocol; absent, the worker holds the canvas on one GPU exactly as before:
+      * ``gpus = 0,1,2,3``  one canvas in row strips over these GPUs, one process per GPU (``main`` re-launches
+        itself under ``torch.distributed.run``; NCCL for the sums, CUDA-IPC peer memory for the halo rows).  Rank 0
+        owns the two sockets and tells the other ranks, once per loop turn, which messages arrived; every rank
+        replays them on its strip, rank 0 assembles and sends the iterates.
+      * ``tiles = P``  P strips inside this one process on one GPU (same kernels and flag protocol; what the
+        single-GPU tests exercise).
+    """
 
     def __init__(self, config, model=None):
-        import zmq
-        self._zmq = zmq
-        self.ctx = zmq.Context.instance()
-        self.sock_in = self.ctx.socket(zmq.PULL)
-        self.sock_out = self.ctx.socket(zmq.PUSH)
-        self.sock_in.bind(config['worker_socket'])
-        self.sock_out.connect(config['app_socket'])
+        import torch.distributed as dist
+        self.rank, self.world, self._ctl = 0, 1, None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+            self._ctl = dist.new_group(backend='gloo')       # control messages travel host-to-host, off the GPU streams
+        self._zmq = None
+        self.sock_in = self.sock_out = None
+        if self.rank == 0:
+            import zmq
+            self._zmq = zmq
+            self.ctx = zmq.Context.instance()
+            self.sock_in = self.ctx.socket(zmq.PULL)
+            self.sock_out = self.ctx.socket(zmq.PUSH)
+            self.sock_in.bind(config['worker_socket'])
+            self.sock_out.connect(config['app_socket'])
+        else:
+            self.ctx = None
+            self.sock_out = _NullSocket()
         self.run_should_stop = False
         if model is None:
             base = utils.REPO_DIR
             gpu = config.getint('gpu', fallback=-1) if hasattr(config, 'getint') else int(config.get('gpu', -1))
+            if self.world > 1:
+                gpu = int(os.environ.get('LOCAL_RANK', self.rank))
             model = B200Model(base / config.get('prototxt', 'models/vgg19.prototxt'),
                               base / config.get('caffemodel', 'models/vgg19.caffemodel'), gpu,
                               precision=config.get('precision', None))
-        self.transfer = StyleTransfer(model)
+        tiles = int(config.get('tiles', 1) or 1)
+        if self.world > 1 or tiles > 1:
+            from .tiled import TiledTransfer
+            self.transfer = TiledTransfer(model, local_world=None if self.world > 1 else tiles)
+        else:
+            self.transfer = StyleTransfer(model)
         # wire format of the iterates: the reference's send_pyobj pickles with the default protocol, so an app on
         # an older Python can still read them; `pickle_protocol` in config.ini overrides (5 saves one 12.6 MB copy)
         proto = config.get('pickle_protocol', None) if hasattr(config, 'get') else None
         self.pickle_protocol = int(proto) if proto not in (None, '') else pickle.DEFAULT_PROTOCOL
         self.sock_out.send_pyobj(WorkerReady(layers=self.transfer.model.layers()))
 
+    # ---- message intake.  One process: straight from the socket.  One process per GPU: rank 0 reads the socket
+    # and broadcasts what it got (possibly nothing) once per loop turn; every rank then does the same thing.
+    def _poll(self, block):
+        """Messages to handle now: everything queued (``block`` = False) or the next one (``block`` = True)."""
+        msgs = []
+        if self.rank == 0:
+            zmq = self._zmq
+            try:
+                if block:
+                    msgs.append(self.sock_in.recv_pyobj())
+                while True:
+                    msgs.append(self.sock_in.recv_pyobj(zmq.NOBLOCK))
+            except zmq.ZMQError:
+                pass
+            except pickle.UnpicklingError:
+                logger.error('Invalid message received over ZeroMQ.')
+        if self.world > 1:
+            import torch.distributed as dist
+            box = [msgs]
+            dist.broadcast_object_list(box, src=0, group=self._ctl)
+            msgs = box[0]
+        return msgs
+
     def run(self):
-        zmq = self._zmq
         try:
             while not self.run_should_stop:
-                if self.transfer.is_running:
-                    try:
-                        while True:
-                            msg = self.sock_in.recv_pyobj(zmq.NOBLOCK)
-                            if self.process_message(msg):
-                                self.run_should_stop = True
-                                break
-                    except zmq.ZMQError:
-                        if self.transfer.is_running:
-                            if self.transfer.check_consistency():
-                                # one iterate stays in flight: iteration t+1 is enqueued before iterate t is
-                                # waited for, pickled and sent, so the transport overlaps the compute
-                                handle = self.transfer.step_async()
-                                self._flush()
-                                self._pending = handle
-                            else:
-                                self._flush()
-                                self.sock_out.send_pyobj(GetImages())
-                    if not self.transfer.is_running:
-                        self._flush()
-                    continue
-                self._flush()
-                msg = self.sock_in.recv_pyobj()
-                if self.process_message(msg):
+                running = self.transfer.is_running
+                for msg in self._poll(block=not running):
+                    if self.process_message(msg):
+                        self.run_should_stop = True
+                        break
+                if self.run_should_stop:
                     break
+                if running and self.transfer.is_running:
+                    if self.transfer.check_consistency():
+                        # one iterate stays in flight: iteration t+1 is enqueued before iterate t is
+                        # waited for, pickled and sent, so the transport overlaps the compute
+                        handle = self.transfer.step_async()
+                        self._flush()
+                        self._pending = handle
+                    else:
+                        self._flush()
+                        self.sock_out.send_pyobj(GetImages())
+                if not self.transfer.is_running:
+                    self._flush()
         except KeyboardInterrupt:
             pass
         finally:
@@ -585,6 +637,8 @@ class Worker:
         handle, self._pending = self._pending, None
         if handle is not None:
             image, trace = handle.result()
+            if image is None:                # a rank that does not assemble iterates (row strips, rank > 0)
+                return
             # `image` is a view of a pinned double buffer: pickling copies it out right here, before the buffer can
             # be reused, so no intermediate np.array() copy; one frame, as recv_pyobj on the app side expects
             # (send_pyobj would pickle with the default protocol and then copy the 12.6 MB frame once more).
@@ -611,10 +665,7 @@ class Worker:
             if msg.reset_state:
                 tr.reset()
         elif isinstance(msg, SetOptimizer):
-            tr.optimizer_cls = SetOptimizer.classes[msg.optimizer]
-            tr.set_step_size(msg.step_size)
-            if not isinstance(tr.optimizer, tr.optimizer_cls):
-                tr.reset()
+            tr.set_optimizer_class(SetOptimizer.classes[msg.optimizer], msg.step_size)
         elif isinstance(msg, SetWeights):
             tr.set_weights(msg.weights, msg.params)
         elif isinstance(msg, Shutdown):
@@ -629,11 +680,44 @@ class Worker:
         return False
 
 
+class _NullSocket:
+    """Outbound socket of the ranks that do not talk to the app."""
+
+    def send_pyobj(self, obj):
+        pass
+
+    def send(self, *args, **kwargs):
+        pass
+
+
+def _gpu_list(config):
+    raw = (config.get('gpus', '') or '').replace(' ', '')
+    return [int(v) for v in raw.split(',') if v != '']
+
+
 def main():
     """worker.py:412-428."""
     messages.install_as_toplevel()
     args = utils.parse_args(__doc__)
     config = utils.read_config(args)
+    gpus = _gpu_list(config)
+    if len(gpus) > 1 and 'WORLD_SIZE' not in os.environ:
+        # `gpus = 0,1,...`: the same command line, one process per GPU (the app starts `worker.py` as one process,
+        # app.py:336-344); rendezvous on the loopback interface
+        import socket
+        s = socket.socket()
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+        s.close()
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=','.join(str(g) for g in gpus))
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(len(gpus)),
+               '--master-addr', '127.0.0.1', '--master-port', str(port), '-m', 'style_transfer2_b200.worker'] + sys.argv[1:]
+        os.execvpe(sys.executable, cmd, env)
+    if int(os.environ.get('WORLD_SIZE', 1)) > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get('LOCAL_RANK', 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     debug = args.debug + config.getint('debug', 0)
     utils.setup_logging(debug)
     utils.setup_signals()
@@ -643,7 +727,7 @@ def main():
         worker.run()
     finally:
         logger.info('Shutting down worker process.')
-        if worker is not None:
+        if worker is not None and worker.ctx is not None:
             worker.ctx.destroy(0)
 
 

@@ -18,7 +18,11 @@ def _port():
     return p
 
 
-def test_worker_speaks_the_reference_protocol(golden):
+@pytest.mark.parametrize('extra', [{}, {'tiles': '2'}], ids=['one-plan', 'two-strips'])
+def test_worker_speaks_the_reference_protocol(golden, extra):
+    """The same scripted app against the whole-canvas worker and against a worker whose canvas is split into two row
+    strips (config key ``tiles``: the tiling scheduler behind the unchanged protocol, incl. the optimizer swap and
+    the RESAMPLE scale change on sharded state)."""
     zmq = pytest.importorskip('zmq')
     from style_transfer2_b200 import messages as m
     from style_transfer2_b200 import vgg
@@ -27,6 +31,7 @@ def test_worker_speaks_the_reference_protocol(golden):
     g = golden('small')
     cfg = {'worker_socket': 'tcp://127.0.0.1:%d' % _port(), 'app_socket': 'tcp://127.0.0.1:%d' % _port(),
            'gpu': '0', 'precision': 'fp16'}
+    cfg.update(extra)
     ctx = zmq.Context.instance()
     app_in = ctx.socket(zmq.PULL)
     app_in.bind(cfg['app_socket'])

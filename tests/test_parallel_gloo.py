@@ -142,3 +142,113 @@ def test_strip_reductions_reproduce_the_whole_canvas_world2(tmp_path):
     port = _free_port()
     mp.spawn(_strip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / ('s%d.txt' % r)).read() for r in range(2)] == ['ok 0 32', 'ok 32 48']
+
+
+class _FakeTransfer:
+    """Records what the worker loop drives (the real ones need a GPU)."""
+
+    def __init__(self):
+        self.is_running = False
+        self.log = []
+        self.t = 0
+
+    def check_consistency(self):
+        return True
+
+    def start(self):
+        self.is_running = True
+        self.log.append('start')
+        return True
+
+    def pause(self):
+        self.is_running = False
+        self.log.append('pause')
+
+    def set_weights(self, weights, params):
+        self.log.append(('weights', sorted(weights)))
+
+    def set_optimizer_class(self, cls, step_size):
+        self.log.append(('optimizer', cls.__name__, step_size))
+
+    def step_async(self):
+        self.t += 1
+        self.log.append(('step', self.t))
+        t = self.t
+
+        class Handle:
+            def result(self_inner):
+                import numpy as np
+                return (np.zeros((2, 2, 3), np.float32) if self.rank0 else None), {'loss': 1.0, 'fevals': t}
+        h = Handle()
+        h.t = t
+        return h
+
+
+def _worker_loop_rank(rank, world, port, zport_in, zport_out, out_dir):
+    """Rank 0 owns the ZeroMQ sockets and broadcasts what arrives; every rank replays the same messages and takes the
+    same steps (style_transfer2_b200.worker.Worker with ``gpus = ...``), here with a recording stand-in transfer."""
+    import pickle
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from style_transfer2_b200 import messages as m
+        from style_transfer2_b200 import worker as wk
+        m.install_as_toplevel()
+        w = wk.Worker.__new__(wk.Worker)
+        w.rank, w.world, w._ctl = rank, world, dist.new_group(backend='gloo')
+        w.run_should_stop = False
+        w.pickle_protocol = pickle.DEFAULT_PROTOCOL
+        w.transfer = _FakeTransfer()
+        w.transfer.rank0 = rank == 0
+        if rank == 0:
+            import zmq
+            w._zmq = zmq
+            w.ctx = zmq.Context.instance()
+            w.sock_in = w.ctx.socket(zmq.PULL)
+            w.sock_out = w.ctx.socket(zmq.PUSH)
+            w.sock_in.bind('tcp://127.0.0.1:%d' % zport_in)
+            w.sock_out.connect('tcp://127.0.0.1:%d' % zport_out)
+        else:
+            w._zmq, w.ctx, w.sock_in, w.sock_out = None, None, None, wk._NullSocket()
+        w.run()
+        with open(os.path.join(out_dir, 'w%d.txt' % rank), 'w') as f:
+            f.write(repr(w.transfer.log))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_worker_replays_messages_on_every_rank_world2(tmp_path):
+    zmq = pytest.importorskip('zmq')
+    from style_transfer2_b200 import messages as m
+    m.install_as_toplevel()
+    port, zin, zout = _free_port(), _free_port(), _free_port()
+    ctx = zmq.Context.instance()
+    app_in = ctx.socket(zmq.PULL)
+    app_in.bind('tcp://127.0.0.1:%d' % zout)
+    app_in.RCVTIMEO = 60000
+    app_out = ctx.socket(zmq.PUSH)
+    app_out.connect('tcp://127.0.0.1:%d' % zin)
+    procs = mp.spawn(_worker_loop_rank, args=(2, port, zin, zout, str(tmp_path)), nprocs=2, join=False)
+    try:
+        app_out.send_pyobj(m.SetWeights({'content': {}, 'style': {}, 'deepdream': {}}, {}))
+        app_out.send_pyobj(m.SetOptimizer('adam'))
+        app_out.send_pyobj(m.StartIteration())
+        seen = []
+        while len(seen) < 3:
+            it = app_in.recv_pyobj()
+            assert isinstance(it, m.Iterate)
+            seen.append(it.i)
+        assert seen == [1, 2, 3]
+        app_out.send_pyobj(m.PauseIteration())
+        app_out.send_pyobj(m.Shutdown())
+        while not isinstance(app_in.recv_pyobj(), m.Shutdown):
+            pass
+        procs.join(60)
+    finally:
+        app_in.close(0)
+        app_out.close(0)
+    logs = [eval(open(tmp_path / ('w%d.txt' % r)).read()) for r in range(2)]
+    assert logs[0] == logs[1]                                   # same messages, same steps, in the same order
+    assert logs[0][:3] == [('weights', ['content', 'deepdream', 'style']), ('optimizer', 'AdamOptimizer', 10), 'start']
+    assert ('step', 3) in logs[0] and logs[0][-1] == 'pause'

@@ -3,7 +3,12 @@
 to ``Worker`` over real ZeroMQ PUSH/PULL sockets; every iterate is deprocessed, copied to the host, pickled
 (H x W x 3 fp32 = 12.6 MB at 1024^2), sent, received and unpickled (worker.py:351-353, app.py:293-323).
 
-    python tools/worker_bench.py [--size 1024] [--iterates 100] [--transport ipc|tcp]
+    python tools/worker_bench.py [--size 1024] [--iterates 100] [--transport ipc|tcp] [--tiles P | --gpus 0,1,..]
+
+``--gpus 0,1,...`` starts the worker the way app.py does -- ``python -m style_transfer2_b200.worker <config>`` as a
+child process -- with a config file carrying ``gpus = ...``: the worker re-launches itself as one process per GPU and
+serves ONE canvas in row strips (rank 0 owns the sockets).  ``--tiles P`` keeps one process and splits the canvas
+into P strips on one GPU.
 """
 import argparse
 import json
@@ -36,6 +41,8 @@ def main():
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--iterates', type=int, default=100)
     ap.add_argument('--transport', default='ipc', choices=['ipc', 'tcp'])
+    ap.add_argument('--tiles', type=int, default=1)
+    ap.add_argument('--gpus', default='')
     args = ap.parse_args()
     m.install_as_toplevel()
     if args.transport == 'ipc':
@@ -44,13 +51,26 @@ def main():
     else:
         cfg = {'worker_socket': 'tcp://127.0.0.1:%d' % _port(), 'app_socket': 'tcp://127.0.0.1:%d' % _port()}
     cfg.update(gpu='0', precision='fp16')
+    if args.tiles > 1:
+        cfg['tiles'] = str(args.tiles)
     ctx = zmq.Context.instance()
     app_in = ctx.socket(zmq.PULL)
     app_in.bind(cfg['app_socket'])
     app_out = ctx.socket(zmq.PUSH)
     app_out.connect(cfg['worker_socket'])
     app_in.RCVTIMEO = 300000
-    th = threading.Thread(target=lambda: Worker(cfg).run(), daemon=True)
+    child = None
+    if args.gpus:
+        import subprocess
+        cfg['gpus'] = args.gpus
+        path = os.path.join(tempfile.mkdtemp(), 'worker.ini')
+        with open(path, 'w') as f:
+            f.write('[DEFAULT]\n' + ''.join('%s = %s\n' % kv for kv in cfg.items()))
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        child = subprocess.Popen([sys.executable, '-m', 'style_transfer2_b200.worker', path], cwd=root)
+        th = threading.Thread(target=child.wait, daemon=True)
+    else:
+        th = threading.Thread(target=lambda: Worker(cfg).run(), daemon=True)
     th.start()
     assert isinstance(app_in.recv_pyobj(), m.WorkerReady)
     content, style, x0 = bench.load_images(args.size)
@@ -69,6 +89,8 @@ def main():
     app_out.send_pyobj(m.Shutdown())
     th.join(30)
     print(json.dumps({'what': 'whole worker over ZeroMQ (%s), every iterate delivered to the app' % args.transport,
+                      'placement': ('row strips over GPUs %s, one process per GPU' % args.gpus) if args.gpus else
+                                   ('%d row strips in one process' % args.tiles if args.tiles > 1 else 'one plan'),
                       'canvas': [args.size, args.size], 'iterates': args.iterates, 'iterations_per_s': args.iterates / dt,
                       'ms_per_iterate': 1e3 * dt / args.iterates, 'iterate_bytes': nbytes // args.iterates,
                       'last_i': it.i, 'last_loss': it.trace['loss']}))
