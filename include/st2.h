@@ -75,7 +75,7 @@ long long st2_launch_count(st2_ctx* ctx);       /* kernels launched so far throu
 /* per-category device timing with CUDA events on the launch stream (off by default).  Categories:
  * 0 tcgen05 conv 3x3 (fwd+dgrad), 1 conv1_1 fwd/dgrad, 2 pool fwd/bwd, 3 Gram, 4 style gradient,
  * 5 loss reductions/combine, 6 pixel terms, 7 optimizer, 8 exact fp32 conv, 9 halo exchange (row strips:
- * peer stores + the wait for the neighbours' rows).
+ * peer stores + the wait for the neighbours' rows), 10 the one launch that finishes all Grams of an evaluation.
  * st2_profile_read SYNCHRONISES, writes elapsed milliseconds and span counts (ST2_PROF_CATS each)
  * accumulated since the last read, and clears them. */
 #define ST2_PROF_CATS 12

@@ -16,7 +16,7 @@ SCAL_TOTAL = SCAL_GLOBAL_BASE + 32
 PREC_FP32, PREC_FP16 = 0, 1
 PROF_CATS = 12
 PROF_NAMES = ('conv_tc', 'conv_first', 'pool', 'gram', 'style_grad', 'loss_elementwise', 'pixel_terms',
-              'optimizer', 'conv_exact', 'halo')
+              'optimizer', 'conv_exact', 'halo', 'gram_finalize')
 RESAMPLE_LANCZOS, RESAMPLE_BILINEAR = 0, 1
 # per-blob scalar fields (st2_common.cuh)
 (SB_C_SUMSQ, SB_S_GRAMSQ, SB_S_RAWSQ, SB_D_SUMSQ, SB_C_NORM, SB_S_NORM, SB_D_NORM, SB_C_VALID, SB_S_VALID,

@@ -697,9 +697,14 @@ __device__ __forceinline__ uint64_t smem_desc_patch(uint32_t addr) {
 template <int BN, int KB>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_o, const ConvGeom g, const float* __restrict__ bias,
+                  const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_a2,
+                  const ConvGeom g, const float* __restrict__ bias,
                   const __half* __restrict__ act, __half* __restrict__ out, const int epi, const TcInject inj) {
   using C = WsCfg<BN, KB>;
+  // <16, 2>: conv1_1 data gradient from TWO 64-channel tensors (the gradient through tmap_a, conv1_1's activations
+  // through tmap_a2) with their own weight halves and their own accumulators (TMEM columns 0..15 / 16..31 of the
+  // slot): gx = acc1 + coef[1] * acc2 -- the style gradient of conv1_1 never exists as a tensor (st2_net.cu).
+  constexpr bool DUAL = (BN == 16 && KB == 2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;
@@ -719,7 +724,10 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int pt0 = blockIdx.x / g.n_blocks, pt_step = gridDim.x / g.n_blocks;
   const int n_pt = g.tiles_h * g.tiles_w;
 
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); tc::prefetch_tmap(&tmap_o); }
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); tc::prefetch_tmap(&tmap_o);
+    if (DUAL) tc::prefetch_tmap(&tmap_a2);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
@@ -753,7 +761,8 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc::mbar_arrive(&full_bar[stage]);
           } else {
             tc::mbar_expect_tx(&full_bar[stage], kPatchBytes);
-            tc::tma_load_3d(smem_p + stage * kPatchBytes, &tmap_a, &full_bar[stage], kb * BK, w0 - 1, h0 - 1 + g.hoff);
+            tc::tma_load_3d(smem_p + stage * kPatchBytes, (DUAL && kb == 1) ? &tmap_a2 : &tmap_a, &full_bar[stage],
+                            DUAL ? 0 : kb * BK, w0 - 1, h0 - 1 + g.hoff);
           }
         }
         __syncwarp();
@@ -787,7 +796,8 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint64_t b_desc = b_desc0 + (uint64_t)(((kb * 9 + tap) * C::kWTile) >> 4);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              tc::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | tap | k) != 0);
+              tc::umma_f16(d_tmem + (DUAL ? kb * 16 : 0), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                           DUAL ? (tap | k) != 0 : (kb | tap | k) != 0);
           }
           tc::umma_commit(&empty_bar[stage]);
         }
@@ -828,12 +838,10 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (valid) {
           float* gx = reinterpret_cast<float*>(out);
           const long long plane = (long long)g.H * g.W, p = (long long)h * g.W + w;
-          if (inj.coef != nullptr) {
-            // second pass over the same gradient planes: gx += coef[1] * acc (the style gradient of conv1_1 folded
-            // into this convolution's weights, see st2_net.cu style_fold_kernel)
-            gx[p] = fmaf(sc, __uint_as_float(r[0]), gx[p]);
-            gx[plane + p] = fmaf(sc, __uint_as_float(r[1]), gx[plane + p]);
-            gx[2 * plane + p] = fmaf(sc, __uint_as_float(r[2]), gx[2 * plane + p]);
+          if (DUAL) {
+            gx[p] = fmaf(sc, __uint_as_float(r[16]), __uint_as_float(r[0]));
+            gx[plane + p] = fmaf(sc, __uint_as_float(r[17]), __uint_as_float(r[1]));
+            gx[2 * plane + p] = fmaf(sc, __uint_as_float(r[18]), __uint_as_float(r[2]));
           } else {
             gx[p] = __uint_as_float(r[0]);
             gx[plane + p] = __uint_as_float(r[1]);
@@ -1183,6 +1191,8 @@ template <int KB> struct WspCfg {
 
 struct TcConvPlan {
   CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap_a2;          // dual-source plans only (tc_conv_dual_plan_create)
+  bool dual = false;
   ConvGeom g;
   int bn;
   int ws_kb;        // > 0: weight-stationary halo-reuse kernel with this many 64-channel K blocks
@@ -1370,7 +1380,7 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   if (per_nb < 1) per_nb = 1;
   p->g.dbg = ctx->debug_flags;
   tc_conv_ws_kernel<BN, KB><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
-      p->tmap_a, p->tmap_b, p->tmap_o, p->g, bias, act, out, epi, inj);
+      p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, p->g, bias, act, out, epi, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1403,11 +1413,45 @@ static int launch_wsp(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __ha
   return 0;
 }
 
-int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* accum_coef) {
-  if (!p || p->bn != 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef) {
+  if (!p || p->bn != 16 || (p->dual != (dual_coef != nullptr)))
+    return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
   TcInject inj;
-  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = accum_coef; inj.pool = nullptr; inj.pool_wp = 0;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = dual_coef; inj.pool = nullptr; inj.pool_wp = 0;
+  if (p->dual) return launch_ws<16, 2>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
   return launch_ws<16, 1>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
+}
+
+int tc_conv_dual_plan_create(st2_ctx* ctx, const __half* grad, const __half* act, const __half* w_dual, int H, int W,
+                             TcConvPlan** out, int halo) {
+  if (W < 16 || H < 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: canvas too small for the conv1_1 gradient kernel");
+  TcConvPlan* p = new TcConvPlan();
+  ConvGeom& g = p->g;
+  g.H = H; g.W = W; g.cin = 128; g.cout = 16; g.taps = 9;       // cin = 128: 64 gradient + 64 activation channels
+  g.hoff = halo;
+  g.TW = kWsTW; g.TH = kWsTH;
+  g.tiles_h = (H + g.TH - 1) / g.TH;
+  g.tiles_w = (W + g.TW - 1) / g.TW;
+  p->bn = 16; p->ws_kb = 2; p->pair = false; p->dual = true;
+  g.n_blocks = 1;
+  g.total_tiles = g.tiles_h * g.tiles_w;
+  g.cblocks = 2;
+  g.k_iters = 18;
+  g.step_nb = g.step_tw = g.step_th = 0; g.dbg = 0;
+  cuuint64_t dims[3] = {64, (cuuint64_t)W, (cuuint64_t)(H + 2 * halo)};
+  cuuint64_t strides[2] = {128, (cuuint64_t)W * 128};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)kPatchW, (cuuint32_t)kPatchH};
+  int rc = st2_encode_tmap(ctx, &p->tmap_a, grad, 3, dims, strides, box);
+  if (!rc) rc = st2_encode_tmap(ctx, &p->tmap_a2, act, 3, dims, strides, box);
+  if (!rc) {
+    cuuint64_t wd[2] = {9 * 128, 16};
+    cuuint64_t ws[1] = {9 * 128 * 2};
+    cuuint32_t wb[2] = {(cuuint32_t)BK, 16};
+    rc = st2_encode_tmap(ctx, &p->tmap_b, w_dual, 2, wd, ws, wb);
+  }
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return 0;
 }
 
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
@@ -1451,10 +1495,11 @@ static St2SmemReg g_smem_conv_tc({
     {ST2_KFN(tc_conv_kernel<64>), Cfg<64>::kSmemBytes},
     {ST2_KFN(tc_conv_ws_kernel<64, 1>), WsCfg<64, 1>::kSmemBytes}, {ST2_KFN(tc_conv_ws_kernel<128, 1>), WsCfg<128, 1>::kSmemBytes},
     {ST2_KFN(tc_conv_ws_kernel<64, 2>), WsCfg<64, 2>::kSmemBytes}, {ST2_KFN(tc_conv_ws_kernel<16, 1>), WsCfg<16, 1>::kSmemBytes},
+    {ST2_KFN(tc_conv_ws_kernel<16, 2>), WsCfg<16, 2>::kSmemBytes},
     {ST2_KFN(tc_conv2_kernel<256>), PairCfg<256>::kSmemBytes}, {ST2_KFN(tc_conv2_kernel<128>), PairCfg<128>::kSmemBytes},
     {ST2_KFN(tc_conv_wsp_kernel<1>), WspCfg<1>::kSmemBytes}, {ST2_KFN(tc_conv_wsp_kernel<2>), WspCfg<2>::kSmemBytes}});
 static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>),
                                       ST2_KFN(tc_conv_ws_kernel<64, 1>), ST2_KFN(tc_conv_ws_kernel<128, 1>),
-                                      ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>),
+                                      ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>), ST2_KFN(tc_conv_ws_kernel<16, 2>),
                                       ST2_KFN(tc_conv2_kernel<256>), ST2_KFN(tc_conv2_kernel<128>),
                                       ST2_KFN(tc_conv_wsp_kernel<1>), ST2_KFN(tc_conv_wsp_kernel<2>)});

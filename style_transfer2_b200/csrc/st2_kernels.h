@@ -86,8 +86,13 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
                    float out_scale, double* sumsq, const TcInject* inj = nullptr, bool* pooled = nullptr);
 // conv1_1 data gradient on the tensor cores: plan made with cin = 64, cout = 16 (the 3 image planes padded),
 // weights [16][tap'][64] fp16; writes fp32 NCHW (3 dense planes of H x W)
-// accum_coef != nullptr: gx += accum_coef[1] * conv (second pass with other weights over the same output planes)
-int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* accum_coef = nullptr);
+// dual plan (tc_conv_dual_plan_create): gx = convT_W(grad) + dual_coef[1] * convT_W'(act) in one launch
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef = nullptr);
+// conv1_1 data gradient with TWO 64-channel sources: the gradient w.r.t. conv1_1 and conv1_1's activations (the style
+// gradient folded into the weights, st2_net.cu style_fold_kernel).  w_dual: [16][9][128] fp16 (channels 0..63 for
+// `grad`, 64..127 for `act`); separate accumulators, combined in the epilogue with a device scalar.
+int tc_conv_dual_plan_create(st2_ctx* ctx, const __half* grad, const __half* act, const __half* w_dual, int H, int W,
+                             TcConvPlan** out, int halo = 0);
 // ---- st2_conv_first_tc.cu: conv1_1 forward on the tensor cores (sliding-window K over pixel pairs) ---------
 struct TcFirstPlan;
 int tc_first_plan_create(st2_ctx* ctx, int H, int W, int halo_strip, TcFirstPlan** out);

@@ -126,38 +126,44 @@ __global__ void style_scale_kernel(const float* __restrict__ D, __half* __restri
 // the data-gradient kernel makes a second pass over F with W' (accumulating into the fp32 gradient planes).
 // The trace value and the normaliser need sum s^2, which needs no s either:
 //     sum_p |D' F_p|^2 = <D'^T D', F^T F> = <D'^T D', (D + A) C HW>      (D' = ds D, the scaled copy as before).
-// One block; D stays in L1.
-__global__ void __launch_bounds__(256)
+// 32 blocks x 128 threads: one (j, k) pair of D'^T D' per thread; D (16 KB) stays in L1 / L2.
+// wdual: the data-gradient weights of conv1_1 as [16 rows][9 taps][128]: channels 0..63 = W (gradient channels,
+// written once at plan creation), 64..127 = W' (activation channels, rewritten here every evaluation).
+__global__ void __launch_bounds__(128)
 style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ w_oihw,
-                  __half* __restrict__ wfold, double n_total, double share, double* sb, double* raw_sum) {
+                  __half* __restrict__ wdual, double n_total, double share, double* sb, double* raw_sum) {
   constexpr int C = 64;
-  __shared__ double red[8];
   const double rms = sqrt(sb[SB_S_GRAMSQ] / (double)(C * C));
   float ds = 1.0f;
   if (rms > 0.0 && isfinite(rms)) ds = exp2f(-ceilf(log2f((float)rms * (float)C)));
-  if (threadIdx.x == 0) sb[SB_S_DSCALE] = (double)ds;
-  for (int idx = threadIdx.x; idx < 3 * 9 * C; idx += blockDim.x) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // 0 .. 4095
+  if (idx == 0) sb[SB_S_DSCALE] = (double)ds;
+  if (idx < 3 * 9 * C) {
     const int j = idx % C, tapf = (idx / C) % 9, plane = idx / (9 * C);
     const int r = 2 - tapf / 3, sx = 2 - tapf % 3;              // tap' = flipped tap of the forward weights
     float acc = 0.f;
-    for (int i = 0; i < C; ++i) acc = fmaf(w_oihw[((i * 3 + plane) * 3 + r) * 3 + sx], D[i * C + j], acc);
-    wfold[(plane * 9 + tapf) * C + j] = __float2half_rn(acc * ds);
+#pragma unroll 8
+    for (int i = 0; i < C; ++i) acc = fmaf(__ldg(w_oihw + ((i * 3 + plane) * 3 + r) * 3 + sx), __ldg(D + i * C + j), acc);
+    wdual[(plane * 9 + tapf) * 128 + 64 + j] = __float2half_rn(acc * ds);
   }
   double tot = 0.0;
-  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+  if (idx < C * C) {
     const int j = idx / C, k = idx % C;
     double e = 0.0;
-    for (int i = 0; i < C; ++i) e += (double)D[i * C + j] * (double)D[i * C + k];
-    tot += e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0));
+#pragma unroll 8
+    for (int i = 0; i < C; ++i) e += (double)__ldg(D + i * C + j) * (double)__ldg(D + i * C + k);
+    tot = e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0));
   }
   tot = warp_sum_d(tot);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    atomicAdd(raw_sum, t * (double)ds * (double)ds * n_total * share);
-  }
+  if ((threadIdx.x & 31) == 0) atomicAdd(raw_sum, tot * (double)ds * (double)ds * n_total * share);
+}
+
+// conv1_1 data-gradient weights [16][9][64] -> the gradient-channel half of the dual pack [16][9][128]
+__global__ void dual_pack_kernel(const __half* __restrict__ wbwd, __half* __restrict__ wdual) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 16 * 9 * 64) return;
+  const int j = idx % 64, rt = idx / 64;
+  wdual[rt * 128 + j] = wbwd[idx];
 }
 
 // worker.py:249-277: freeze normalisers on first use, derive combine coefficients and trace values
@@ -237,8 +243,8 @@ struct Blob {
   TcConvPlan* tc_fwd = nullptr;   // producing this blob (conv blobs, idx >= 1)
   TcConvPlan* tc_bwd = nullptr;   // consuming grad of this blob, producing grad of the blob below
   TcConvPlan* tc_style = nullptr;
-  TcConvPlan* tc_sfold = nullptr;  // conv1_1: second data-gradient pass over the activations with the folded weights
-  __half* wfold = nullptr;         // conv1_1: W' = W D (16 x 9 x 64 fp16, rows 3..15 zero)
+  TcConvPlan* tc_sfold = nullptr;  // conv1_1: data gradient with two sources (gradient + activations), dual weights
+  __half* wfold = nullptr;         // conv1_1: [16][9][128] fp16: W for the gradient channels | W' = W D for the activations
   TcGramPlan* tc_gram = nullptr;
   TcFirstPlan* tc_first = nullptr; // conv1_1 only
   long long n() const { return (long long)C * H * W; }
@@ -575,11 +581,9 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
     if (is_conv) {
       const int ci = g_blobs[i].conv_index;
       if (ci == 0 && cur.tc_bwd) {
-        rc = tc_conv_first_bwd_launch(ctx, cur.tc_bwd, grad_out);
-        if (!rc && inj[i].fold) {
-          ProfScope ps2(ctx, 4);
-          rc = tc_conv_first_bwd_launch(ctx, cur.tc_sfold, grad_out, inj[i].coef);
-        }
+        // fold: ONE launch reads the gradient and the activations (two patches per tile, two accumulators)
+        rc = inj[i].fold ? tc_conv_first_bwd_launch(ctx, cur.tc_sfold, grad_out, inj[i].coef)
+                         : tc_conv_first_bwd_launch(ctx, cur.tc_bwd, grad_out);
       } else if (ci == 0) {
         rc = launch_conv_first_bwd<T>(ctx, (const T*)cur.grad, ctx->wf32_bwd[0], grad_out, cur.H, cur.W, lo, hi);
       } else if (pl->prec == ST2_PREC_FP32) {
@@ -748,7 +752,7 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
     pl->inj[b].coef = sb + SB_C_COEF;          // [C_COEF, S_COEF, D_COEF] are consecutive
   }
   if (n_gram) {
-    ProfScope ps(ctx, 3);
+    ProfScope ps(ctx, 10);
     if ((rc = tc_gram_finalize_all(ctx, n_gram, gp, gA, gD, gS, pl->strip ? 1 : 0))) return rc;
   }
   pl->eval_phase = 1;
@@ -778,15 +782,18 @@ static int eval_mid_impl(st2_plan* pl) {
     ProfScope ps(ctx, 4);
     if (b == 1 && B.tc_bwd != nullptr && pl->prec == ST2_PREC_FP16 && !ctx->knobs.no_style_fuse) {
       if (!B.wfold) {
-        if ((rc = ensure(ctx, (void**)&B.wfold, sizeof(__half) * 16 * 9 * 64))) return rc;
-        ST2_CUDA(ctx, cudaMemsetAsync(B.wfold, 0, sizeof(__half) * 16 * 9 * 64, ctx->stream));
+        if ((rc = ensure(ctx, (void**)&B.wfold, sizeof(__half) * 16 * 9 * 128))) return rc;
+        ST2_CUDA(ctx, cudaMemsetAsync(B.wfold, 0, sizeof(__half) * 16 * 9 * 128, ctx->stream));
+        dual_pack_kernel<<<cdiv(16 * 9 * 64, 256), 256, 0, ctx->stream>>>(ctx->wh_bwd[0], B.wfold);
+        ST2_LAUNCH_CHECK(ctx);
       }
-      if (!B.tc_sfold && (rc = tc_conv_plan_create(ctx, (const __half*)(pl->strip ? B.act_pad : B.act), B.wfold, B.H, B.W, 64,
-                                                   16, 9, &B.tc_sfold, pl->strip ? 1 : 0)))
+      if (!B.tc_sfold && (rc = tc_conv_dual_plan_create(ctx, (const __half*)(pl->strip ? B.grad_pad : B.grad),
+                                                        (const __half*)(pl->strip ? B.act_pad : B.act), B.wfold, B.H, B.W,
+                                                        &B.tc_sfold, pl->strip ? 1 : 0)))
         return rc;
       // on strips every rank derives the same total from the all-reduced Gram: each contributes 1 / world of it
-      style_fold_kernel<<<1, 256, 0, ctx->stream>>>(B.D, B.gram_target, ctx->w_oihw[0], B.wfold, B.n_total(),
-                                                    1.0 / (double)pl->world, sb, raw_sum);
+      style_fold_kernel<<<32, 128, 0, ctx->stream>>>(B.D, B.gram_target, ctx->w_oihw[0], B.wfold, B.n_total(),
+                                                     1.0 / (double)pl->world, sb, raw_sum);
       ST2_LAUNCH_CHECK(ctx);
       pl->inj[b].sraw = nullptr;
       pl->inj[b].fold = true;
@@ -1388,5 +1395,5 @@ int st2_gram_nchw(st2_ctx* ctx, const float* x, int C, long long HW, float* out)
 }  // extern "C"
 
 static St2KernelReg g_reg_net({ST2_KFN(halo_exchange_kernel), ST2_KFN(pack_x_kernel),
-                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(style_fold_kernel), ST2_KFN(scatter_sums_kernel),
+                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(style_fold_kernel), ST2_KFN(dual_pack_kernel), ST2_KFN(scatter_sums_kernel),
                                   ST2_KFN(coef_kernel), ST2_KFN(final_kernel), ST2_KFN(pack_weights_kernel)});
