@@ -19,6 +19,7 @@
 #include "st2_tc.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -48,7 +49,71 @@ struct ConvGeom {
   int step_nb, step_tw, step_th;   // decomposition of gridDim.x in (n block, tile column, tile row) digits
   int hoff;  // row strips: the tensor map starts `hoff` halo rows above the first output row
   int dbg;   // st2_debug_flags(): 1 no epilogue stores, 2 no MMA, 4 no A loads, 8 no B loads (timing experiments)
+  int rot;   // 1: tile rows are visited in the order 1, 2, .., tiles_h - 1, 0 (the two that touch halo rows last)
+  HaloArgs halo;
 };
+
+// tile row visited at position `th` of the schedule
+__device__ __forceinline__ int rot_row(const ConvGeom& g, int th) {
+  return g.rot ? (th + 1 == g.tiles_h ? 0 : th + 1) : th;
+}
+// does the tile row at schedule position `th` read a halo row?
+__device__ __forceinline__ bool halo_row(const ConvGeom& g, int th) { return g.rot && th >= g.tiles_h - 2; }
+
+// All threads of the first push_blocks CTAs, at kernel start.
+__device__ __forceinline__ void halo_push_prologue(const HaloArgs& h) {
+  if (h.push_blocks == 0) return;
+  const int npush = h.push_blocks < (int)gridDim.x ? h.push_blocks : (int)gridDim.x;
+  if ((int)blockIdx.x >= npush) return;
+  const long long n16 = h.bytes >> 4;
+#pragma unroll
+  for (int dir = 0; dir < 2; ++dir) {
+    if (h.dst[dir] == nullptr) continue;
+    const uint4* s4 = reinterpret_cast<const uint4*>(h.src[dir]);
+    uint4* d4 = reinterpret_cast<uint4*>(h.dst[dir]);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)npush * blockDim.x)
+      d4[i] = s4[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(h.counter, 1u);
+    if (prev == (unsigned int)npush - 1) {
+      atomicExch(h.counter, 0u);
+      __threadfence_system();
+#pragma unroll
+      for (int dir = 0; dir < 2; ++dir)
+        if (h.flag[dir] != nullptr)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(h.flag[dir]), "l"(h.epoch) : "memory");
+    }
+  }
+}
+
+// One lane of the TMA producer warp, right before the first tile that reads a halo row.
+__device__ __forceinline__ void halo_wait_flags(const HaloArgs& h) {
+#pragma unroll
+  for (int dir = 0; dir < 2; ++dir) {
+    const unsigned long long* f = h.wait[dir];
+    if (f == nullptr || *reinterpret_cast<volatile int*>(h.err) != 0) continue;
+    unsigned long long t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= h.epoch) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) { atomicExch(h.err, 1); break; }     // 10 s: the neighbour died; fail loudly
+      __nanosleep(32);
+    }
+  }
+}
+// whole producer warp: returns true once the halo rows are known to be in place
+__device__ __forceinline__ bool halo_ready(const ConvGeom& g, bool waited, int th) {
+  if (waited || !halo_row(g, th)) return waited;
+  if ((threadIdx.x & 31) == 0) halo_wait_flags(g.halo);
+  __syncwarp();
+  asm volatile("fence.proxy.async;" ::: "memory");       // the rows are read by the TMA unit (async proxy)
+  return true;
+}
 
 // Tile coordinates advanced by gridDim.x per step without divisions (mixed-radix add with carry).
 struct TileWalk {
@@ -238,6 +303,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
@@ -259,11 +325,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // whole warp runs the (uniform) loop; one elected lane issues expect_tx + the TMA loads of a stage
     int stage = 0; uint32_t phase = 0;
     const bool three = (g.taps == 9);
+    bool waited = false;
     TileWalk tk;
     tk.init(g, blockIdx.x);
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, tk.next(g)) {
       const int nb = tk.nb;
-      const int h0 = tk.th * g.TH, w0 = tk.tw * g.TW;
+      waited = halo_ready(g, waited, tk.th);
+      const int h0 = rot_row(g, tk.th) * g.TH, w0 = tk.tw * g.TW;
       int tap = 0, cb = 0;                               // K block index it = tap * cblocks + cb
       for (int it = 0; it < g.k_iters; it += C::KB) {
         const int nkb = (g.k_iters - it < C::KB) ? g.k_iters - it : C::KB;
@@ -355,7 +423,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int nb = tk.nb;
-      const int h = tk.th * g.TH + row_h;
+      const int h = rot_row(g, tk.th) * g.TH + row_h;
       const int w = tk.tw * g.TW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
@@ -471,6 +539,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); }
   if (warp == 1 && lane == 0) {
@@ -490,10 +559,12 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
     int stage = 0; uint32_t phase = 0;
+    bool waited = false;
     for (int tile = pair; tile < n_tiles; tile += n_pairs) {
       const int nb = tile % g.n_blocks;
       const int pt = tile / g.n_blocks;
-      const int w0 = (pt % g.tiles_w) * g.TW, h0 = (pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH;
+      waited = halo_ready(g, waited, pt / g.tiles_w);
+      const int w0 = (pt % g.tiles_w) * g.TW, h0 = rot_row(g, pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH;
       int tap = 0, cb = 0;
       for (int it = 0; it < g.k_iters; it += KB) {
         const int nkb = (g.k_iters - it < KB) ? g.k_iters - it : KB;
@@ -570,7 +641,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int acc = local & 1;
       const int nb = tile % g.n_blocks;
       const int pt = tile / g.n_blocks;
-      const int h = (pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH + row_h;
+      const int h = rot_row(g, pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH + row_h;
       const int w = (pt % g.tiles_w) * g.TW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
@@ -723,6 +794,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int nb = blockIdx.x % g.n_blocks;
   const int pt0 = blockIdx.x / g.n_blocks, pt_step = gridDim.x / g.n_blocks;
   const int n_pt = g.tiles_h * g.tiles_w;
+  halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); tc::prefetch_tmap(&tmap_o);
@@ -750,8 +822,11 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     __syncwarp();
     int stage = 0; uint32_t phase = 0;
+    bool waited = false;
     for (int pt = pt0; pt < n_pt; pt += pt_step) {
-      const int th = pt / g.tiles_w, tw = pt - th * g.tiles_w;
+      const int ths = pt / g.tiles_w, tw = pt - ths * g.tiles_w;
+      waited = halo_ready(g, waited, ths);
+      const int th = rot_row(g, ths);
       const int h0 = th * kWsTH, w0 = tw * kWsTW;
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
@@ -823,7 +898,8 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int pt = pt0; pt < n_pt; pt += pt_step, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int th = pt / g.tiles_w, tw = pt - th * g.tiles_w;
+      const int ths = pt / g.tiles_w, tw = pt - ths * g.tiles_w;
+      const int th = rot_row(g, ths);
       const int h = th * kWsTH + row_h, w = tw * kWsTW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
@@ -859,7 +935,8 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // immediately needed, so their latency (not their bandwidth) is what the epilogue pays
         const int ptn = pt + pt_step;
         if (ptn < n_pt) {
-          const int thn = ptn / g.tiles_w, twn = ptn - thn * g.tiles_w;
+          const int thns = ptn / g.tiles_w, twn = ptn - thns * g.tiles_w;
+          const int thn = rot_row(g, thns);
           const int hn = thn * kWsTH + row_h, wn = twn * kWsTW + row_w;
           if (hn < g.H && wn < g.W) {
             const long long on = ((long long)hn * g.W + wn) * g.cout + (long long)nb * BN;
@@ -1252,6 +1329,8 @@ int tc_conv_plan_create(st2_ctx* ctx, const __half* in, const __half* w_packed, 
   ConvGeom& g = p->g;
   g.H = H; g.W = W; g.cin = cin; g.cout = cout; g.taps = taps;
   g.hoff = halo;                 // `in` then points at the first halo row; H counts the output rows only
+  g.rot = 0;
+  memset(&g.halo, 0, sizeof(g.halo));
   g.TW = (W <= 4) ? 4 : (W <= 8 ? 8 : 16);
   g.TH = BM / g.TW;
   g.tiles_h = (H + g.TH - 1) / g.TH;
@@ -1413,9 +1492,17 @@ static int launch_wsp(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __ha
   return 0;
 }
 
-int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef) {
+static void set_halo(TcConvPlan* p, const HaloArgs* halo) {
+  if (halo != nullptr && halo->push_blocks > 0) { p->g.halo = *halo; p->g.rot = 1; }
+  else { memset(&p->g.halo, 0, sizeof(p->g.halo)); p->g.rot = 0; }
+}
+
+bool tc_conv_supports_halo(const TcConvPlan* p) { return p != nullptr && !(p->ws_kb && p->pair); }
+
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef, const HaloArgs* halo) {
   if (!p || p->bn != 16 || (p->dual != (dual_coef != nullptr)))
     return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
+  set_halo(p, halo);
   TcInject inj;
   inj.fc = nullptr; inj.sraw = nullptr; inj.coef = dual_coef; inj.pool = nullptr; inj.pool_wp = 0;
   if (p->dual) return launch_ws<16, 2>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
@@ -1438,6 +1525,8 @@ int tc_conv_dual_plan_create(st2_ctx* ctx, const __half* grad, const __half* act
   g.cblocks = 2;
   g.k_iters = 18;
   g.step_nb = g.step_tw = g.step_th = 0; g.dbg = 0;
+  g.rot = 0;
+  memset(&g.halo, 0, sizeof(g.halo));
   cuuint64_t dims[3] = {64, (cuuint64_t)W, (cuuint64_t)(H + 2 * halo)};
   cuuint64_t strides[2] = {128, (cuuint64_t)W * 128};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)kPatchW, (cuuint32_t)kPatchH};
@@ -1455,8 +1544,11 @@ int tc_conv_dual_plan_create(st2_ctx* ctx, const __half* grad, const __half* act
 }
 
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
-                   float out_scale, double* sumsq, const TcInject* inj_in, bool* pooled) {
+                   float out_scale, double* sumsq, const TcInject* inj_in, bool* pooled, const HaloArgs* halo) {
   if (epi == EPI_BIAS_RELU && !bias) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: bias required");
+  if (halo != nullptr && halo->push_blocks > 0 && !tc_conv_supports_halo(p))
+    return st2_fail(ctx, ST2_ERR_STATE, "tc_conv: this kernel has no in-kernel halo exchange");
+  set_halo(p, halo);
   if (epi == EPI_MASK && !act) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: act required");
   TcInject inj;
   inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr; inj.pool = nullptr; inj.pool_wp = 0;

@@ -69,6 +69,24 @@ int pixel_terms_strip(st2_ctx* ctx, const float* x, long long xps, int wrap, con
                       int C, int H, int W, float tv, float tv_power, float p, float p_power, float divisor,
                       double* scal, double* part = nullptr, unsigned int* counter = nullptr);
 
+// ---- row strips: halo rows pushed and awaited INSIDE the consuming convolution kernel -------------------------
+// (one process per GPU; st2_net.cu halo_args).  At kernel start the first `push_blocks` CTAs store this strip's first /
+// last row of the tensor the kernel is about to convolve into the neighbours' halo rows (peer memory) and the last of
+// them raises the neighbours' flags; the kernel then works through its tiles with the tile rows that touch a halo row
+// scheduled LAST, and its TMA producer polls this strip's own flags only right before the first of those tiles -- by
+// then the neighbours' rows have long arrived.  No exchange launch, no wait on the critical path.
+struct HaloArgs {
+  const unsigned char* src[2];          // my first / last interior row (dir 0: goes to the strip above, 1: below)
+  unsigned char* dst[2];                // halo row over there; nullptr: no neighbour on that side
+  unsigned long long* flag[2];          // flag to raise over there
+  const unsigned long long* wait[2];    // my flags (raised by the strip above / below); nullptr: canvas edge
+  long long bytes;                      // one row
+  unsigned long long epoch;
+  unsigned int* counter;                // in my slab header; 0 between kernels
+  int* err;                             // sticky: a wait timed out
+  int push_blocks;                      // 0: nothing to do (not a strip / old exchange kernel used)
+};
+
 // ---- st2_conv_tc.cu (tcgen05 implicit GEMM, fp16 NHWC) -----------------------------------------
 struct TcConvPlan;     // tensor maps + tile geometry for one (layer, direction, canvas)
 // halo = 1 (row strips): `in` points at a buffer of H + 2 rows whose first and last row are halo rows
@@ -83,11 +101,15 @@ void tc_conv_plan_destroy(TcConvPlan* p);
 // per row) from the same epilogue; *pooled (tc_conv_launch) tells whether the launched kernel did it
 struct TcInject { const __half* fc; const __half* sraw; const double* coef; __half* pool; int pool_wp; };
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
-                   float out_scale, double* sumsq, const TcInject* inj = nullptr, bool* pooled = nullptr);
+                   float out_scale, double* sumsq, const TcInject* inj = nullptr, bool* pooled = nullptr,
+                   const HaloArgs* halo = nullptr);
+// does the kernel this plan launches carry the in-kernel halo push / wait?
+bool tc_conv_supports_halo(const TcConvPlan* p);
 // conv1_1 data gradient on the tensor cores: plan made with cin = 64, cout = 16 (the 3 image planes padded),
 // weights [16][tap'][64] fp16; writes fp32 NCHW (3 dense planes of H x W)
 // dual plan (tc_conv_dual_plan_create): gx = convT_W(grad) + dual_coef[1] * convT_W'(act) in one launch
-int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef = nullptr);
+int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef = nullptr,
+                             const HaloArgs* halo = nullptr);
 // conv1_1 data gradient with TWO 64-channel sources: the gradient w.r.t. conv1_1 and conv1_1's activations (the style
 // gradient folded into the weights, st2_net.cu style_fold_kernel).  w_dual: [16][9][128] fp16 (channels 0..63 for
 // `grad`, 64..127 for `act`); separate accumulators, combined in the epilogue with a device scalar.

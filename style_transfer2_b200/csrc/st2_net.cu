@@ -276,6 +276,7 @@ struct SlabHeader {
   unsigned long long flag_from[2][kSlots];     // [0]: raised by the strip above, [1]: by the strip below
   unsigned int counters[2];
   int err;                                     // sticky: a wait timed out
+  unsigned int push_counter;                   // in-kernel halo push (HaloArgs::counter)
 };
 static_assert(sizeof(SlabHeader) <= kSlabHeader, "slab header");
 
@@ -393,6 +394,7 @@ struct st2_plan {
   size_t esz;
   // row-strip state (strip == false: the plan holds the whole canvas)
   bool strip = false, edge_top = true, edge_bot = true;
+  bool async_halo = false;     // halo rows travel inside the consuming convolution kernels (all neighbours over IPC)
   int rank = 0, world = 1, row0 = 0, H_total = 0;
   unsigned char* slab = nullptr;
   StripLayout lay;
@@ -479,6 +481,42 @@ static int halo_exchange(st2_plan* pl, int slot) {
   return 0;
 }
 
+// One process per GPU (every neighbour attached through CUDA IPC): the exchange of `slot` is carried by the
+// convolution kernel that consumes the tensor (HaloArgs, st2_kernels.h) instead of a launch of its own.  Several strips
+// of one process on one GPU keep the exchange kernel: CTAs spinning inside a convolution would starve the other
+// strips' kernels of SMs.
+static bool halo_args(st2_plan* pl, int slot, HaloArgs* a) {
+  memset(a, 0, sizeof(*a));
+  if (!pl->strip || !pl->async_halo || slot == 0 || !pl->peer[0] || !pl->peer[1]) return false;
+  const bool up = !pl->edge_top, dn = !pl->edge_bot;
+  if (!up && !dn) return false;
+  const int b = slot % ST2_NUM_BLOBS;
+  const bool is_grad = slot >= ST2_NUM_BLOBS;
+  SlabHeader* mine = reinterpret_cast<SlabHeader*>(pl->slab);
+  const StripLayout& L = pl->lay;
+  const size_t rb = L.row_bytes[b];
+  if (rb % 16) return false;
+  a->epoch = ++pl->epoch[slot];
+  a->bytes = (long long)rb;
+  a->counter = &mine->push_counter;
+  a->err = &mine->err;
+  a->push_blocks = (int)((rb / 16 + 255) / 256);
+  if (a->push_blocks > 16) a->push_blocks = 16;
+  if (a->push_blocks < 1) a->push_blocks = 1;
+  const unsigned char* base = pl->slab + (is_grad ? L.grad_off[b] : L.act_off[b]);
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? up : dn)) continue;
+    const StripLayout& PL = pl->peer_lay[side];
+    SlabHeader* theirs = reinterpret_cast<SlabHeader*>(pl->peer[side]);
+    a->flag[side] = &theirs->flag_from[side == 0 ? 1 : 0][slot];
+    a->wait[side] = &mine->flag_from[side][slot];
+    a->src[side] = base + (side == 0 ? (size_t)1 : (size_t)L.rows[b]) * rb;
+    unsigned char* pbase = pl->peer[side] + (is_grad ? PL.grad_off[b] : PL.act_off[b]);
+    a->dst[side] = pbase + (side == 0 ? (size_t)(PL.rows[b] + 1) * rb : 0);
+  }
+  return true;
+}
+
 template <typename T>
 static int forward_impl(st2_plan* pl, const float* x, int top) {
   st2_ctx* ctx = pl->ctx;
@@ -523,8 +561,12 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
         TcInject ti;
         ti.fc = nullptr; ti.sraw = nullptr; ti.coef = nullptr; ti.pool = nullptr; ti.pool_wp = 0;
         if (i + 1 <= top && g_blobs[i + 1].kind == KIND_POOL) { ti.pool = (__half*)pl->b[i + 1].act; ti.pool_wp = pl->b[i + 1].W; }
+        // row strips: this kernel also carries the exchange of its input's boundary rows (or the exchange kernel ran
+        // after the producer, see the end of the loop body)
+        HaloArgs ha;
+        const bool carried = tc_conv_supports_halo(cur.tc_fwd) && halo_args(pl, i - 1, &ha);
         rc = tc_conv_launch(ctx, cur.tc_fwd, ctx->bias[ci], nullptr, (__half*)cur.act, EPI_BIAS_RELU, 1.f, nullptr, &ti,
-                            &pool_fused);
+                            &pool_fused, carried ? &ha : nullptr);
       }
     } else if (pool_fused) {
       pool_fused = false;                       // written by the convolution below
@@ -533,7 +575,11 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
     }
     if (rc) return rc;
     // the next convolution reads one row of the neighbouring strips
-    if (pl->strip && i < top && g_blobs[i + 1].kind == KIND_CONV && (rc = halo_exchange(pl, i))) return rc;
+    if (pl->strip && i < top && g_blobs[i + 1].kind == KIND_CONV) {
+      const bool in_kernel = pl->async_halo && pl->prec == ST2_PREC_FP16 && g_blobs[i + 1].conv_index > 0 &&
+                             tc_conv_supports_halo(pl->b[i + 1].tc_fwd) && pl->lay.row_bytes[i] % 16 == 0;
+      if (!in_kernel && (rc = halo_exchange(pl, i))) return rc;
+    }
   }
   pl->x_cur = x;
   pl->top_cur = top;
@@ -575,15 +621,23 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
     const bool below_conv = g_blobs[i - 1].kind == KIND_CONV;
     const int mask_below = (below_conv && !inj[i - 1].on) ? 1 : 0;
     const int bcat = !is_conv ? 2 : (g_blobs[i].conv_index == 0 ? 1 : (pl->prec == ST2_PREC_FP32 ? 8 : 0));
-    // the data-gradient convolution reads one row of the neighbouring strips' gradient
-    if (pl->strip && is_conv && (rc = halo_exchange(pl, ST2_NUM_BLOBS + i))) return rc;
+    // the data-gradient convolution reads one row of the neighbouring strips' gradient: carried by the kernel itself
+    // where it can be, else by the exchange kernel
+    HaloArgs ha;
+    bool carried = false;
+    if (pl->strip && is_conv) {
+      const bool tc_consumer = pl->prec == ST2_PREC_FP16 && cur.tc_bwd != nullptr && tc_conv_supports_halo(cur.tc_bwd);
+      carried = tc_consumer && halo_args(pl, ST2_NUM_BLOBS + i, &ha);
+      if (!carried && (rc = halo_exchange(pl, ST2_NUM_BLOBS + i))) return rc;
+    }
+    const HaloArgs* hap = carried ? &ha : nullptr;
     ProfScope ps(ctx, bcat);
     if (is_conv) {
       const int ci = g_blobs[i].conv_index;
       if (ci == 0 && cur.tc_bwd) {
         // fold: ONE launch reads the gradient and the activations (two patches per tile, two accumulators)
-        rc = inj[i].fold ? tc_conv_first_bwd_launch(ctx, cur.tc_sfold, grad_out, inj[i].coef)
-                         : tc_conv_first_bwd_launch(ctx, cur.tc_bwd, grad_out);
+        rc = inj[i].fold ? tc_conv_first_bwd_launch(ctx, cur.tc_sfold, grad_out, inj[i].coef, hap)
+                         : tc_conv_first_bwd_launch(ctx, cur.tc_bwd, grad_out, nullptr, hap);
       } else if (ci == 0) {
         rc = launch_conv_first_bwd<T>(ctx, (const T*)cur.grad, ctx->wf32_bwd[0], grad_out, cur.H, cur.W, lo, hi);
       } else if (pl->prec == ST2_PREC_FP32) {
@@ -594,11 +648,11 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
         ti.fc = (const __half*)inj[i - 1].fc; ti.sraw = (const __half*)inj[i - 1].sraw; ti.coef = inj[i - 1].coef;
         ti.pool = nullptr; ti.pool_wp = 0;
         rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad, EPI_MASK, 1.f,
-                            nullptr, &ti);
+                            nullptr, &ti, nullptr, hap);
         fused_inj = true;
       } else {
         rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad,
-                            mask_below ? EPI_MASK : EPI_RAW, 1.f, nullptr);
+                            mask_below ? EPI_MASK : EPI_RAW, 1.f, nullptr, nullptr, nullptr, hap);
       }
     } else {
       rc = launch_pool_bwd_v<T>(ctx, (const T*)below.act, (const T*)cur.grad, (T*)below.grad, below.C, below.H,
@@ -921,6 +975,7 @@ int st2_ctx_create(int device, st2_ctx** out) {
     k.no_pool_fusion = getenv("ST2_NO_POOL_FUSION") != nullptr;
     k.no_style_fuse = getenv("ST2_NO_STYLE_FUSE") != nullptr;
     k.no_graph = getenv("ST2_NO_GRAPH") != nullptr;
+    k.no_inkernel_halo = getenv("ST2_NO_INKERNEL_HALO") != nullptr;
     if (const char* v = getenv("ST2_TC_BN")) k.tc_bn = atoi(v);
     if (const char* v = getenv("ST2_PAIR_MIN_TILES")) k.pair_min_tiles = atoll(v);
   }
@@ -1139,6 +1194,7 @@ int st2_strip_attach(st2_plan* pl, int side, const void* ipc_handle, st2_plan* l
     pl->peer_ipc[side] = true;
   }
   pl->peer_lay[side] = strip_layout(peer_rows, pl->W, pl->esz);
+  pl->async_halo = pl->peer[0] && pl->peer[1] && pl->peer_ipc[0] && pl->peer_ipc[1] && !ctx->knobs.no_inkernel_halo;
   return 0;
 }
 
