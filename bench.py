@@ -375,6 +375,7 @@ def timed_steps(st, steps, barrier, world, eng):
     for _ in range(steps):
         st.step(fetch=False)
     e1.record()
+    timed_steps.host_enqueue_ms = (time.perf_counter() - t0) * 1000.0 / steps      # host time to ENQUEUE one step
     barrier()
     t1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
@@ -404,6 +405,7 @@ def canvas_record(args, rank, world, local, sampler, peaks, barrier):
         job.step(fetch=False)
     ms, launches, t0, t1 = timed_steps(job, steps, barrier, world, eng)
     clocks = sampler.window(t0, t1) if sampler else None
+    host_ms = timed_steps.host_enqueue_ms
     rec.update(value=steps / (ms / 1000.0), unit='it/s', ms_per_step=ms / steps, gpu_launches_per_step=launches / steps,
                clocks=clocks)
 
@@ -425,6 +427,12 @@ def canvas_record(args, rank, world, local, sampler, peaks, barrier):
     regime = regime_of(clocks)
     main, roofs = rooflines_of(cats, size, world, peaks, regime, args.precision, canvas=True)
     rec.update(kernel_time_ms_per_step=cats, roofline=main)
+    if world > 1:
+        # every rank's view: where a strip waits for its neighbours shows up as a longer conv / allreduce span there
+        from style_transfer2_b200 import parallel
+        mine = {'rank': rank, 'host_enqueue_ms_per_step': host_ms,
+                'ms_per_step': {k: round(v['ms_per_step'], 4) for k, v in cats.items()}}
+        rec['per_rank'] = parallel.gather_objects(mine)
     if rank == 0 and hasattr(job, 'traces'):
         rec['loss'] = float(job.traces[-1].loss)
     if world > 1:
@@ -648,6 +656,7 @@ def main():
         done = torch.cuda.Event()
         done.record(main_stream)
         side.wait_event(done)
+        ev = None
         for lo, hi in cuts:
             with torch.cuda.stream(side):
                 xh[lo:hi].copy_(xin[lo:hi], non_blocking=True)          # result -> host
@@ -655,6 +664,7 @@ def main():
                 ev.record(side)
             main_stream.wait_event(ev)
             xin[lo:hi].copy_(xh[lo:hi], non_blocking=True)              # host -> next step's input
+        return ev                                                       # the last read-back chunk has left the device
 
     def e2e_steps(n):
         pending, sink = None, 0.0
@@ -665,8 +675,10 @@ def main():
                 x_round_trip()
                 sink += float(tr['loss'])
                 continue
-            handle = st.step_async()
-            x_round_trip()
+            # x (on the critical path: the next step needs it back) gets the read-back engine first, the iterate image
+            # follows and overlaps the next iteration
+            handle = st.step_async(download=False)
+            handle.download(after=x_round_trip())
             if pending is not None:
                 img, tr = pending.result()
                 sink += float(tr['loss']) + float(img[0, 0, 0])

@@ -168,6 +168,10 @@ int st2_strip_ipc_handle(st2_plan* plan, void* handle_out /* ST2_IPC_HANDLE_BYTE
 /* side 0: the strip above (rank-1, or the last strip for rank 0), side 1: the strip below.  Exactly one of
  * ipc_handle / local_peer is given.  peer_rows: the rows that strip holds. */
 int st2_strip_attach(st2_plan* plan, int side, const void* ipc_handle, st2_plan* local_peer, int peer_rows);
+/* conv1_1's style gradient can be folded into its data-gradient weights instead of being materialised (fp16 path);
+ * grad(conv1_1) then has another meaning, and strips read a row of each other's: enable only when EVERY strip of the
+ * canvas holds >= 16 rows and >= 16 columns (the tensor-core conv1_1 kernels' minimum).  Off by default on strips. */
+int st2_strip_set_fold(st2_plan* plan, int enable);
 /* which 0: Gram sums (fp32), 1: per-blob partial sums (f64), 2: six pixel-space sums (f64) */
 int st2_strip_reduce_block(st2_plan* plan, int which, void** dev_out, long long* count_out);
 /* 1 when a halo wait timed out since the plan was created -- SYNCHRONISES */

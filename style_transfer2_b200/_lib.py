@@ -67,6 +67,7 @@ _SIGS = {
     'st2_strip_plan_create': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     'st2_strip_ipc_handle': (_i, [_vp, _vp]),
     'st2_strip_attach': (_i, [_vp, _i, _vp, _vp, _i]),
+    'st2_strip_set_fold': (_i, [_vp, _i]),
     'st2_strip_reduce_block': (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(C.c_longlong)]),
     'st2_strip_halo_error': (_i, [_vp, _ip]),
     'st2_read_scalars': (_i, [_vp, _dp]),

@@ -63,15 +63,17 @@ __device__ __forceinline__ bool halo_row(const ConvGeom& g, int th) { return g.r
 // All threads of the first push_blocks CTAs, at kernel start.
 __device__ __forceinline__ void halo_push_prologue(const HaloArgs& h) {
   if (h.push_blocks == 0) return;
+  // the LAST CTAs of the grid push: with a partial last wave of tiles they are the ones with a tile less to do
   const int npush = h.push_blocks < (int)gridDim.x ? h.push_blocks : (int)gridDim.x;
-  if ((int)blockIdx.x >= npush) return;
+  const int pb = (int)blockIdx.x - ((int)gridDim.x - npush);
+  if (pb < 0) return;
   const long long n16 = h.bytes >> 4;
 #pragma unroll
   for (int dir = 0; dir < 2; ++dir) {
     if (h.dst[dir] == nullptr) continue;
     const uint4* s4 = reinterpret_cast<const uint4*>(h.src[dir]);
     uint4* d4 = reinterpret_cast<uint4*>(h.dst[dir]);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)npush * blockDim.x)
+    for (long long i = (long long)pb * blockDim.x + threadIdx.x; i < n16; i += (long long)npush * blockDim.x)
       d4[i] = s4[i];
   }
   __threadfence_system();
@@ -1498,6 +1500,7 @@ static void set_halo(TcConvPlan* p, const HaloArgs* halo) {
 }
 
 bool tc_conv_supports_halo(const TcConvPlan* p) { return p != nullptr && !(p->ws_kb && p->pair); }
+
 
 int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef, const HaloArgs* halo) {
   if (!p || p->bn != 16 || (p->dual != (dual_coef != nullptr)))

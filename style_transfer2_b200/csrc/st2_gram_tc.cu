@@ -233,7 +233,10 @@ int tc_gram_plan_create(st2_ctx* ctx, const __half* F, int C, long long HW, TcGr
   g.m_tiles = (C + GM - 1) / GM;
   g.n_tiles = C / p->gn;
   const int tiles = g.m_tiles * g.n_tiles;
-  long long want = ctx->sm_count / tiles;
+  // split-K over all SMs -- but a partial tile is 128 x GN fp32: for C = 512 (8 tiles) a split per SM would write and
+  // re-read 19 MB of partial tiles for a 4-17 MB input; half the splits cost the contraction nothing (it is latency-
+  // bound there) and halve that traffic
+  long long want = ctx->sm_count / tiles / (C >= 512 ? 2 : 1);
   if (want < 1) want = 1;
   long long chunk = (HW + want - 1) / want;
   chunk = (chunk + KP - 1) / KP * KP;

@@ -130,8 +130,12 @@ __global__ void style_scale_kernel(const float* __restrict__ D, __half* __restri
 // wdual: the data-gradient weights of conv1_1 as [16 rows][9 taps][128]: channels 0..63 = W (gradient channels,
 // written once at plan creation), 64..127 = W' (activation channels, rewritten here every evaluation).
 __global__ void __launch_bounds__(128)
-style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ w_oihw,
-                  __half* __restrict__ wdual, double n_total, double share, double* sb, double* raw_sum) {
+style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ gsum_local,
+                  const float* __restrict__ w_oihw, __half* __restrict__ wdual, double n_total, double* sb,
+                  double* raw_sum) {
+  // gsum_local (row strips): THIS strip's un-normalised Gram sum F^T F, so that the strip contributes exactly its own
+  // sum_p |D' F_p|^2 to the all-reduced total (like a strip that does not fold); nullptr: the whole canvas,
+  // F^T F = (D + A) C HW.
   constexpr int C = 64;
   const double rms = sqrt(sb[SB_S_GRAMSQ] / (double)(C * C));
   float ds = 1.0f;
@@ -152,10 +156,11 @@ style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, cons
     double e = 0.0;
 #pragma unroll 8
     for (int i = 0; i < C; ++i) e += (double)__ldg(D + i * C + j) * (double)__ldg(D + i * C + k);
-    tot = e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0));
+    tot = gsum_local != nullptr ? e * (double)gsum_local[idx]
+                                : e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0)) * n_total;
   }
   tot = warp_sum_d(tot);
-  if ((threadIdx.x & 31) == 0) atomicAdd(raw_sum, tot * (double)ds * (double)ds * n_total * share);
+  if ((threadIdx.x & 31) == 0) atomicAdd(raw_sum, tot * (double)ds * (double)ds);
 }
 
 // conv1_1 data-gradient weights [16][9][64] -> the gradient-channel half of the dual pack [16][9][128]
@@ -395,6 +400,7 @@ struct st2_plan {
   // row-strip state (strip == false: the plan holds the whole canvas)
   bool strip = false, edge_top = true, edge_bot = true;
   bool async_halo = false;     // halo rows travel inside the consuming convolution kernels (all neighbours over IPC)
+  bool strip_fold = false;     // every strip of the canvas folds conv1_1's style gradient (st2_strip_set_fold)
   int rank = 0, world = 1, row0 = 0, H_total = 0;
   unsigned char* slab = nullptr;
   StripLayout lay;
@@ -404,6 +410,7 @@ struct st2_plan {
   unsigned long long epoch[kSlots] = {};
   float* xp = nullptr;                               // padded copy of x: 3 x (H + 2) x W
   float* gram_red = nullptr;                         // strip Gram sums, fp32, all-reduced by the caller
+  float* gram_local1 = nullptr;                      // conv1_1's strip Gram sum as it was before the all-reduce (style fold)
   long long gram_red_off[ST2_NUM_BLOBS] = {};
   long long gram_red_used = 0;
   double* red = nullptr;                             // 3 partial sums per blob, all-reduced by the caller
@@ -720,6 +727,18 @@ static int ensure(st2_ctx* ctx, void** p, size_t bytes) {
   return 0;
 }
 
+// The style layer whose gradient s = sc (D F) is folded into the weights of its own data-gradient convolution instead
+// of being materialised (style_fold_kernel): conv1_1 on the fp16 path.  (Tried for conv2_1 as a second, accumulating
+// pass of its 128 -> 64 data-gradient kernel: that pass cost 82 us at 1024^2 against the 41 + 41 us it saved.)
+// On row strips the choice must be the SAME on every strip: with the fold, grad(conv1_1) does not contain the style
+// term, and a strip reads one row of its neighbours' grad(conv1_1) -- so the caller, who knows all strips, says
+// whether every strip can fold (st2_strip_set_fold; a strip shorter than 16 rows cannot run the tensor-core conv1_1
+// kernels).
+static bool fold_eligible(const st2_plan* pl, int b) {
+  return b == 1 && pl->prec == ST2_PREC_FP16 && !pl->ctx->knobs.no_style_fuse && pl->b[b].tc_bwd != nullptr &&
+         (!pl->strip || pl->strip_fold);
+}
+
 // The objective (worker.py:231-301) in four phases.  On a whole-canvas plan st2_eval runs them back to
 // back.  On a row strip the caller all-reduces (sum) one small block between consecutive phases:
 //   begin: forward; local feature sums; the strip's Gram sums            -> all-reduce gram_red (fp32)
@@ -777,7 +796,7 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
     if (s_on) {
       const size_t e = (b == 0) ? sizeof(float) : pl->esz;
       if ((rc = ensure(ctx, (void**)&B.D, sizeof(float) * B.C * B.C))) return rc;
-      if ((rc = ensure(ctx, &B.sraw, e * B.n()))) return rc;
+      if (!fold_eligible(pl, b) && (rc = ensure(ctx, &B.sraw, e * B.n()))) return rc;
       ProfScope ps(ctx, 3);
       if (pl->strip) {
         pl->gram_red_off[b] = pl->gram_red_used;
@@ -809,6 +828,9 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
     ProfScope ps(ctx, 10);
     if ((rc = tc_gram_finalize_all(ctx, n_gram, gp, gA, gD, gS, pl->strip ? 1 : 0))) return rc;
   }
+  if (pl->strip && host_w_on(pl->b[1].sw) && fold_eligible(pl, 1))
+    ST2_CUDA(ctx, cudaMemcpyAsync(pl->gram_local1, pl->gram_red + pl->gram_red_off[1], sizeof(float) * 64 * 64,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
   pl->eval_phase = 1;
   return 0;
 }
@@ -834,7 +856,7 @@ static int eval_mid_impl(st2_plan* pl) {
         return rc;
     }
     ProfScope ps(ctx, 4);
-    if (b == 1 && B.tc_bwd != nullptr && pl->prec == ST2_PREC_FP16 && !ctx->knobs.no_style_fuse) {
+    if (b == 1 && fold_eligible(pl, b)) {
       if (!B.wfold) {
         if ((rc = ensure(ctx, (void**)&B.wfold, sizeof(__half) * 16 * 9 * 128))) return rc;
         ST2_CUDA(ctx, cudaMemsetAsync(B.wfold, 0, sizeof(__half) * 16 * 9 * 128, ctx->stream));
@@ -845,9 +867,8 @@ static int eval_mid_impl(st2_plan* pl) {
                                                         (const __half*)(pl->strip ? B.act_pad : B.act), B.wfold, B.H, B.W,
                                                         &B.tc_sfold, pl->strip ? 1 : 0)))
         return rc;
-      // on strips every rank derives the same total from the all-reduced Gram: each contributes 1 / world of it
-      style_fold_kernel<<<32, 128, 0, ctx->stream>>>(B.D, B.gram_target, ctx->w_oihw[0], B.wfold, B.n_total(),
-                                                     1.0 / (double)pl->world, sb, raw_sum);
+      style_fold_kernel<<<32, 128, 0, ctx->stream>>>(B.D, B.gram_target, pl->strip ? pl->gram_local1 : nullptr,
+                                                     ctx->w_oihw[0], B.wfold, B.n_total(), sb, raw_sum);
       ST2_LAUNCH_CHECK(ctx);
       pl->inj[b].sraw = nullptr;
       pl->inj[b].fold = true;
@@ -1093,6 +1114,7 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
     long long gtot = 0;
     for (int i = 0; i < ST2_NUM_BLOBS; ++i) gtot += (long long)g_blobs[i].channels * g_blobs[i].channels;
     ST2_CUDA(ctx, cudaMalloc(&pl->gram_red, sizeof(float) * gtot));
+    ST2_CUDA(ctx, cudaMalloc(&pl->gram_local1, sizeof(float) * 64 * 64));
   }
   int h = H, w = W, hg = H_total;
   for (int i = 0; i < ST2_NUM_BLOBS; ++i) {
@@ -1198,6 +1220,14 @@ int st2_strip_attach(st2_plan* pl, int side, const void* ipc_handle, st2_plan* l
   return 0;
 }
 
+int st2_strip_set_fold(st2_plan* pl, int enable) {
+  if (!pl || !pl->strip) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_strip_set_fold: not a strip plan");
+  if (enable && pl->prec == ST2_PREC_FP16 && pl->b[1].tc_bwd == nullptr)
+    return st2_fail(pl->ctx, ST2_ERR_STATE, "st2_strip_set_fold: this strip is too small for the tensor-core conv1_1 kernels");
+  pl->strip_fold = enable != 0;
+  return 0;
+}
+
 int st2_strip_reduce_block(st2_plan* pl, int which, void** dev_out, long long* count_out) {
   if (!pl || !pl->strip || !dev_out || !count_out || which < 0 || which > 2)
     return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_strip_reduce_block: bad arguments");
@@ -1227,7 +1257,7 @@ void st2_plan_destroy(st2_plan* pl) {
     tc_gram_plan_destroy(B.tc_gram);
     tc_first_plan_destroy(B.tc_first);
   }
-  cudaFree(pl->slab); cudaFree(pl->red); cudaFree(pl->gram_red);
+  cudaFree(pl->slab); cudaFree(pl->red); cudaFree(pl->gram_red); cudaFree(pl->gram_local1);
   cudaFree(pl->scal); cudaFree(pl->gram_acc); cudaFree(pl->bwd); cudaFree(pl->part); cudaFree(pl->part_counter);
   delete pl;
 }

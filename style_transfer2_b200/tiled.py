@@ -96,6 +96,9 @@ class StripPlan(Plan):
     def eval_final(self):
         self._check(self.lib.st2_eval_final(self.handle), 'st2_eval_final')
 
+    def set_fold(self, enable):
+        self._check(self.lib.st2_strip_set_fold(self.handle, 1 if enable else 0), 'st2_strip_set_fold')
+
     def halo_error(self):
         err = C.c_int()
         self._check(self.lib.st2_strip_halo_error(self.handle, C.byref(err)), 'st2_strip_halo_error')
@@ -204,6 +207,11 @@ class TiledTransfer:
             self.strips.append(st)
         self.engine.sync_stream()
         torch.cuda.synchronize(dev)
+        # conv1_1's style gradient is folded into its data-gradient weights only when EVERY strip can (>= 16 rows):
+        # the strips read a row of each other's grad(conv1_1), which means something else with the fold
+        fold = self.model.precision_name == 'fp16' and self.W >= 16 and min(e - s for s, e in bounds) >= 16
+        for st in self.strips:
+            st.plan.set_fold(fold)
         self._attach()
         self._weights_dirty = True
         self._content_done, self._style_done = set(), set()

@@ -155,10 +155,19 @@ class IterateHandle:
     copy and returns ``(image, trace)`` exactly as ``step()`` does.  The image array is a view of a
     double-buffered pinned block: consume (or copy) it before the second-next ``step_async``."""
 
-    def __init__(self, host, done, trace, t):
+    def __init__(self, host, done, trace, t, start=None):
         self._host, self._done, self.trace, self.t = host, done, trace, t
+        self._start = start              # deferred download (step_async(download=False)): enqueues the copy, returns its event
+
+    def download(self, after=None):
+        """Enqueue the device -> host copy of a handle made with ``step_async(download=False)``; ``after``: an event
+        the copy must wait for (e.g. another read-back that should get the copy engine first)."""
+        if self._start is not None:
+            self._done = self._start(after)
+            self._start = None
 
     def result(self):
+        self.download()
         self._done.synchronize()
         return self._host.numpy(), self.trace.data
 
@@ -253,7 +262,7 @@ class StyleTransfer:
         # steps.  The pipelined path (step_async / IterateHandle) hands out the pinned double buffer itself.
         return np.array(host.numpy())
 
-    def image_async(self, x, trace):
+    def image_async(self, x, trace, download=True):
         """Enqueue deprocess + device->host copy of ``x`` on the download stream; no host wait."""
         dev = self.engine.device
         main = torch.cuda.current_stream(dev)
@@ -271,13 +280,21 @@ class StyleTransfer:
         self.engine.call('st2_deprocess', C.c_void_p(x.data_ptr()), C.c_void_p(d['dev'][k].data_ptr()), h, w)
         ready = torch.cuda.Event()
         ready.record(main)
-        with torch.cuda.stream(d['stream']):
-            d['stream'].wait_event(ready)
-            d['host'][k].copy_(d['dev'][k], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(d['stream'])
-        d['done'][k] = done
-        return IterateHandle(d['host'][k], done, trace, self.t)
+
+        def start(after=None):
+            with torch.cuda.stream(d['stream']):
+                d['stream'].wait_event(ready)
+                if after is not None:
+                    d['stream'].wait_event(after)
+                d['host'][k].copy_(d['dev'][k], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(d['stream'])
+            d['done'][k] = done
+            return done
+
+        if download:
+            return IterateHandle(d['host'][k], start(), trace, self.t)
+        return IterateHandle(d['host'][k], None, trace, self.t, start)
 
     def _pinned_buffer(self, shape):
         for buf in self._pinned:
@@ -507,15 +524,16 @@ class StyleTransfer:
             self._private_plans.clear()
         self._plan = None
 
-    def step_async(self):
+    def step_async(self, download=True):
         """``step()`` without the host wait: returns an ``IterateHandle``.  Lets the caller overlap the
         iterate's trip to the host (12.6 MB at 1024^2) and its own pickling / sending with the next iteration
-        (SURVEY 8f #3: the reference pickles every iterate synchronously, worker.py:351-353)."""
+        (the reference pickles every iterate synchronously, worker.py:351-353).
+        ``download=False``: the image is deprocessed but its copy is only enqueued by ``handle.download(after)``."""
         self.t += 1
         x, _ = self.optimizer.step()
         tr = self.traces[-1]
         tr('fevals', self.t)
-        return self.image_async(x, tr)
+        return self.image_async(x, tr, download)
 
     def write_trace(self, filename):
         df = pd.DataFrame(t.data for t in self.traces)

@@ -75,7 +75,10 @@ def tiled(model, x0, content, style, world, optimizer='lbfgs'):
 
 
 @pytest.mark.parametrize('precision,world,hw', [('fp32', 1, (64, 48)), ('fp32', 2, (64, 80)), ('fp32', 3, (100, 72)),
-                                                ('fp16', 2, (96, 80)), ('fp16', 4, (150, 131)), ('fp16', 1, (48, 64))])
+                                                ('fp16', 2, (96, 80)), ('fp16', 4, (150, 131)), ('fp16', 1, (48, 64)),
+                                                # a ragged 4-row last strip: too short for the tensor-core conv1_1 kernels, so
+                                                # it materialises conv1_1's style gradient while the other strips fold it
+                                                ('fp16', 3, (100, 72))])
 def test_strips_reproduce_the_whole_canvas_objective(models, precision, world, hw):
     m = models(precision)
     x0, content, style = images(*hw)
@@ -93,7 +96,15 @@ def test_strips_reproduce_the_whole_canvas_objective(models, precision, world, h
         if k == 'time':
             continue
         assert np.isclose(tr[k], v, rtol=tol_s), (k, tr[k], v)
-    assert rel_err(grad, grad_ref.cpu().numpy()) < tol_g
+    g_ref = grad_ref.cpu().numpy()
+    per_strip = [round(float(rel_err(grad[:, :, r0:r1], g_ref[:, :, r0:r1])), 5) for r0, r1 in tt.bounds]
+    if precision == 'fp16' and min(r1 - r0 for r0, r1 in tt.bounds) < 16:
+        # a strip shorter than 16 rows runs conv1_1 on the CUDA-core kernels (fp32 arithmetic, not the tensor-core
+        # hi/lo split): last-bit differences in its fp16 activations move ReLU / arg-max decisions in and around that
+        # strip; the bound is the fp16 path's bound against the oracle
+        tol_g = 5e-2
+    assert rel_err(grad, g_ref) < tol_g, per_strip
+    print('strips %s %s: gradient vs un-split plan per strip %s' % (precision, hw, per_strip))
     tt.close()
 
 

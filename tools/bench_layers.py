@@ -14,6 +14,7 @@ import torch
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--size', type=int, default=1024)
+ap.add_argument('--height', type=int, default=0, help='canvas rows (default: --size); e.g. 512 with --size 4096 = the shape of one of 8 row strips')
 ap.add_argument('--flags', default='0')
 ap.add_argument('--reps', type=int, default=20)
 ap.add_argument('--precision', default='fp16')
@@ -23,8 +24,9 @@ from style_transfer2_b200 import vgg
 from style_transfer2_b200.model import B200Model
 
 m = B200Model(precision=args.precision)
-plan = m.plan(args.size, args.size)
-x = torch.randn(1, 3, args.size, args.size, device=m.engine.device) * 50
+H = args.height or args.size
+plan = m.plan(H, args.size)
+x = torch.randn(1, 3, H, args.size, device=m.engine.device) * 50
 plan.forward(x, vgg.BLOB_INDEX['conv5_1'])
 rows = []
 for flags in [int(f) for f in args.flags.split(',')]:
