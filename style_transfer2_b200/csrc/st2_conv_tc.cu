@@ -53,12 +53,16 @@ struct ConvGeom {
   HaloArgs halo;
 };
 
+// The kernels are instantiated with and without the in-kernel halo exchange (template parameter HALO): measured on
+// one box, the few per-tile instructions of the exchange cost the whole-canvas launches ~2 % when merely compiled in.
 // tile row visited at position `th` of the schedule
+template <bool HALO>
 __device__ __forceinline__ int rot_row(const ConvGeom& g, int th) {
-  return g.rot ? (th + 1 == g.tiles_h ? 0 : th + 1) : th;
+  return HALO ? (th + 1 == g.tiles_h ? 0 : th + 1) : th;
 }
 // does the tile row at schedule position `th` read a halo row?
-__device__ __forceinline__ bool halo_row(const ConvGeom& g, int th) { return g.rot && th >= g.tiles_h - 2; }
+template <bool HALO>
+__device__ __forceinline__ bool halo_row(const ConvGeom& g, int th) { return HALO && th >= g.tiles_h - 2; }
 
 // All threads of the first push_blocks CTAs, at kernel start.
 __device__ __forceinline__ void halo_push_prologue(const HaloArgs& h) {
@@ -109,8 +113,9 @@ __device__ __forceinline__ void halo_wait_flags(const HaloArgs& h) {
   }
 }
 // whole producer warp: returns true once the halo rows are known to be in place
+template <bool HALO>
 __device__ __forceinline__ bool halo_ready(const ConvGeom& g, bool waited, int th) {
-  if (waited || !halo_row(g, th)) return waited;
+  if (!HALO || waited || !halo_row<HALO>(g, th)) return waited;
   if ((threadIdx.x & 31) == 0) halo_wait_flags(g.halo);
   __syncwarp();
   asm volatile("fence.proxy.async;" ::: "memory");       // the rows are read by the TMA unit (async proxy)
@@ -285,7 +290,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
       *reinterpret_cast<uint4*>(out_c + (long long)(j - me) * pix_stride + me * 8) = o4[j];
 }
 
-template <int BN>
+template <int BN, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
@@ -305,7 +310,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  halo_push_prologue(g.halo);
+  if (HALO) halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
@@ -332,8 +337,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tk.init(g, blockIdx.x);
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, tk.next(g)) {
       const int nb = tk.nb;
-      waited = halo_ready(g, waited, tk.th);
-      const int h0 = rot_row(g, tk.th) * g.TH, w0 = tk.tw * g.TW;
+      waited = halo_ready<HALO>(g, waited, tk.th);
+      const int h0 = rot_row<HALO>(g, tk.th) * g.TH, w0 = tk.tw * g.TW;
       int tap = 0, cb = 0;                               // K block index it = tap * cblocks + cb
       for (int it = 0; it < g.k_iters; it += C::KB) {
         const int nkb = (g.k_iters - it < C::KB) ? g.k_iters - it : C::KB;
@@ -425,7 +430,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int nb = tk.nb;
-      const int h = rot_row(g, tk.th) * g.TH + row_h;
+      const int h = rot_row<HALO>(g, tk.th) * g.TH + row_h;
       const int w = tk.tw * g.TW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
@@ -516,7 +521,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // both shared memories, so per SM the operand traffic from shared memory drops from (128 + BN) to
 // (128 + BN / 2) rows per K step -- the single-CTA kernel at N = 256 is at ~96 B/clk of the 128 B/clk shared
 // memory port.  The pair tile is 16 rows x 16 pixels; CTA rank r owns rows 8r .. 8r+7 of it.
-template <int BN>
+template <int BN, bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
@@ -541,7 +546,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  halo_push_prologue(g.halo);
+  if (HALO) halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); }
   if (warp == 1 && lane == 0) {
@@ -565,8 +570,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int tile = pair; tile < n_tiles; tile += n_pairs) {
       const int nb = tile % g.n_blocks;
       const int pt = tile / g.n_blocks;
-      waited = halo_ready(g, waited, pt / g.tiles_w);
-      const int w0 = (pt % g.tiles_w) * g.TW, h0 = rot_row(g, pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH;
+      waited = halo_ready<HALO>(g, waited, pt / g.tiles_w);
+      const int w0 = (pt % g.tiles_w) * g.TW, h0 = rot_row<HALO>(g, pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH;
       int tap = 0, cb = 0;
       for (int it = 0; it < g.k_iters; it += KB) {
         const int nkb = (g.k_iters - it < KB) ? g.k_iters - it : KB;
@@ -643,7 +648,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int acc = local & 1;
       const int nb = tile % g.n_blocks;
       const int pt = tile / g.n_blocks;
-      const int h = rot_row(g, pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH + row_h;
+      const int h = rot_row<HALO>(g, pt / g.tiles_w) * (2 * g.TH) + (int)rank * g.TH + row_h;
       const int w = (pt % g.tiles_w) * g.TW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
@@ -767,7 +772,7 @@ __device__ __forceinline__ uint64_t smem_desc_patch(uint32_t addr) {
   return d;
 }
 
-template <int BN, int KB>
+template <int BN, int KB, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_a2,
@@ -796,7 +801,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int nb = blockIdx.x % g.n_blocks;
   const int pt0 = blockIdx.x / g.n_blocks, pt_step = gridDim.x / g.n_blocks;
   const int n_pt = g.tiles_h * g.tiles_w;
-  halo_push_prologue(g.halo);
+  if (HALO) halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); tc::prefetch_tmap(&tmap_o);
@@ -827,8 +832,8 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     bool waited = false;
     for (int pt = pt0; pt < n_pt; pt += pt_step) {
       const int ths = pt / g.tiles_w, tw = pt - ths * g.tiles_w;
-      waited = halo_ready(g, waited, ths);
-      const int th = rot_row(g, ths);
+      waited = halo_ready<HALO>(g, waited, ths);
+      const int th = rot_row<HALO>(g, ths);
       const int h0 = th * kWsTH, w0 = tw * kWsTW;
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
@@ -901,7 +906,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int ths = pt / g.tiles_w, tw = pt - ths * g.tiles_w;
-      const int th = rot_row(g, ths);
+      const int th = rot_row<HALO>(g, ths);
       const int h = th * kWsTH + row_h, w = tw * kWsTW + row_w;
       const bool valid = (h < g.H) && (w < g.W) && !(g.dbg & 1);
       const long long obase = ((long long)h * g.W + w) * g.cout + (long long)nb * BN;
@@ -938,7 +943,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int ptn = pt + pt_step;
         if (ptn < n_pt) {
           const int thns = ptn / g.tiles_w, twn = ptn - thns * g.tiles_w;
-          const int thn = rot_row(g, thns);
+          const int thn = rot_row<HALO>(g, thns);
           const int hn = thn * kWsTH + row_h, wn = twn * kWsTW + row_w;
           if (hn < g.H && wn < g.W) {
             const long long on = ((long long)hn * g.W + wn) * g.cout + (long long)nb * BN;
@@ -1437,8 +1442,12 @@ static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   p->g.step_nb = grid % p->g.n_blocks;
   p->g.step_tw = (grid / p->g.n_blocks) % p->g.tiles_w;
   p->g.step_th = (grid / p->g.n_blocks) / p->g.tiles_w;
-  tc_conv_kernel<BN><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias,
-                                                                              act, out, epi, out_scale, sumsq, inj);
+  if (p->g.rot)
+    tc_conv_kernel<BN, true><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act,
+                                                                                      out, epi, out_scale, sumsq, inj);
+  else
+    tc_conv_kernel<BN, false><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act,
+                                                                                       out, epi, out_scale, sumsq, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1460,8 +1469,12 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   if (per_nb > n_pt) per_nb = n_pt;
   if (per_nb < 1) per_nb = 1;
   p->g.dbg = ctx->debug_flags;
-  tc_conv_ws_kernel<BN, KB><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
-      p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, p->g, bias, act, out, epi, inj);
+  if (p->g.rot)
+    tc_conv_ws_kernel<BN, KB, true><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
+        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, p->g, bias, act, out, epi, inj);
+  else
+    tc_conv_ws_kernel<BN, KB, false><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
+        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, p->g, bias, act, out, epi, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1473,7 +1486,10 @@ static int launch_pair(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __h
   int pairs = ctx->sm_count / 2;
   if (pairs > p->g.total_tiles) pairs = p->g.total_tiles;
   p->g.dbg = ctx->debug_flags;
-  tc_conv2_kernel<BN><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
+  if (p->g.rot)
+    tc_conv2_kernel<BN, true><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
+  else
+    tc_conv2_kernel<BN, false><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1585,16 +1601,45 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
   }
 }
 
+#define ST2_BOTH(K, ...) {ST2_KFN(K<__VA_ARGS__, false>), SM}, {ST2_KFN(K<__VA_ARGS__, true>), SM}
 static St2SmemReg g_smem_conv_tc({
-    {ST2_KFN(tc_conv_kernel<256>), Cfg<256>::kSmemBytes}, {ST2_KFN(tc_conv_kernel<128>), Cfg<128>::kSmemBytes},
-    {ST2_KFN(tc_conv_kernel<64>), Cfg<64>::kSmemBytes},
-    {ST2_KFN(tc_conv_ws_kernel<64, 1>), WsCfg<64, 1>::kSmemBytes}, {ST2_KFN(tc_conv_ws_kernel<128, 1>), WsCfg<128, 1>::kSmemBytes},
-    {ST2_KFN(tc_conv_ws_kernel<64, 2>), WsCfg<64, 2>::kSmemBytes}, {ST2_KFN(tc_conv_ws_kernel<16, 1>), WsCfg<16, 1>::kSmemBytes},
-    {ST2_KFN(tc_conv_ws_kernel<16, 2>), WsCfg<16, 2>::kSmemBytes},
-    {ST2_KFN(tc_conv2_kernel<256>), PairCfg<256>::kSmemBytes}, {ST2_KFN(tc_conv2_kernel<128>), PairCfg<128>::kSmemBytes},
+#define SM Cfg<256>::kSmemBytes
+    ST2_BOTH(tc_conv_kernel, 256),
+#undef SM
+#define SM Cfg<128>::kSmemBytes
+    ST2_BOTH(tc_conv_kernel, 128),
+#undef SM
+#define SM Cfg<64>::kSmemBytes
+    ST2_BOTH(tc_conv_kernel, 64),
+#undef SM
+#define SM WsCfg<64, 1>::kSmemBytes
+    ST2_BOTH(tc_conv_ws_kernel, 64, 1),
+#undef SM
+#define SM WsCfg<128, 1>::kSmemBytes
+    ST2_BOTH(tc_conv_ws_kernel, 128, 1),
+#undef SM
+#define SM WsCfg<64, 2>::kSmemBytes
+    ST2_BOTH(tc_conv_ws_kernel, 64, 2),
+#undef SM
+#define SM WsCfg<16, 1>::kSmemBytes
+    ST2_BOTH(tc_conv_ws_kernel, 16, 1),
+#undef SM
+#define SM WsCfg<16, 2>::kSmemBytes
+    ST2_BOTH(tc_conv_ws_kernel, 16, 2),
+#undef SM
+#define SM PairCfg<256>::kSmemBytes
+    ST2_BOTH(tc_conv2_kernel, 256),
+#undef SM
+#define SM PairCfg<128>::kSmemBytes
+    ST2_BOTH(tc_conv2_kernel, 128),
+#undef SM
     {ST2_KFN(tc_conv_wsp_kernel<1>), WspCfg<1>::kSmemBytes}, {ST2_KFN(tc_conv_wsp_kernel<2>), WspCfg<2>::kSmemBytes}});
-static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_kernel<256>), ST2_KFN(tc_conv_kernel<128>), ST2_KFN(tc_conv_kernel<64>),
-                                      ST2_KFN(tc_conv_ws_kernel<64, 1>), ST2_KFN(tc_conv_ws_kernel<128, 1>),
-                                      ST2_KFN(tc_conv_ws_kernel<64, 2>), ST2_KFN(tc_conv_ws_kernel<16, 1>), ST2_KFN(tc_conv_ws_kernel<16, 2>),
-                                      ST2_KFN(tc_conv2_kernel<256>), ST2_KFN(tc_conv2_kernel<128>),
+#undef ST2_BOTH
+#define ST2_BOTH(K, ...) ST2_KFN(K<__VA_ARGS__, false>), ST2_KFN(K<__VA_ARGS__, true>)
+static St2KernelReg g_reg_conv_tc({ST2_BOTH(tc_conv_kernel, 256), ST2_BOTH(tc_conv_kernel, 128), ST2_BOTH(tc_conv_kernel, 64),
+                                      ST2_BOTH(tc_conv_ws_kernel, 64, 1), ST2_BOTH(tc_conv_ws_kernel, 128, 1),
+                                      ST2_BOTH(tc_conv_ws_kernel, 64, 2), ST2_BOTH(tc_conv_ws_kernel, 16, 1),
+                                      ST2_BOTH(tc_conv_ws_kernel, 16, 2), ST2_BOTH(tc_conv2_kernel, 256),
+                                      ST2_BOTH(tc_conv2_kernel, 128),
                                       ST2_KFN(tc_conv_wsp_kernel<1>), ST2_KFN(tc_conv_wsp_kernel<2>)});
+#undef ST2_BOTH
