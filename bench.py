@@ -637,48 +637,64 @@ def main():
     value = jobs * args.steps / (ms / 1000.0)
 
     # ---- end-to-end arm: the public step API with HOST buffers.  Every step's input x comes from pinned host
-    # memory and every step's result -- the new x (next step's input: a true data dependency), the iterate image
-    # (HxWx3 fp32) and the trace -- is read back to pinned host memory.  The image travels on a side stream while the
-    # next iteration computes (StyleTransfer.step_async), as in the worker loop.  The x round trip (device -> host ->
-    # device, 2 x 12.6 MB at 1024^2) is cut into four chunks so that the read-back of chunk c+1 (one copy engine)
-    # overlaps the upload of chunk c (the other): ~0.31 ms instead of 0.5 ms on the critical path.  The host reads
-    # the loss and a pixel of every iterate.
+    # memory (H2D) and every step's result -- the new x, the iterate image (HxWx3 fp32) and the trace -- is read
+    # back to pinned host memory (D2H).  The copies are pipelined against the compute the way a data loader
+    # prefetches the next batch: L-BFGS fixes the new iterate x_{k+1} right at the START of step k+1 (x += s), the
+    # evaluation that follows only reads it -- so x_{k+1} is read back (4 chunks, side stream) and uploaded again
+    # from the host buffer into a staging tensor (second copy engine) while that evaluation runs, and step k+2 starts
+    # from the staging tensor (one device copy of 12.6 MB).  The iterate image goes down after x, overlapping the
+    # next iteration (StyleTransfer.step_async, as in the worker loop).  The host reads the loss and a pixel of every
+    # iterate.  The strips workload keeps the simple form (round trip after the step).
     x_host = torch.empty(st.input.shape, dtype=torch.float32, pin_memory=True)
     x_host.copy_(st.input)
+    x_stage = torch.empty_like(st.input)
     torch.cuda.synchronize()
     main_stream = torch.cuda.current_stream()
-    side = torch.cuda.Stream()
-    xin, xh = st.input.view(-1), x_host.view(-1)
+    side, up = torch.cuda.Stream(), torch.cuda.Stream()
+    xin, xh, xs = st.input.view(-1), x_host.view(-1), x_stage.view(-1)
     n_el = xin.numel()
     cuts = [(i * n_el // 4, (i + 1) * n_el // 4) for i in range(4)]
+    flight = {'down': None, 'up': None}
 
-    def x_round_trip():
+    def x_round_trip(x=None, into=None):
+        """new x -> pinned host (side stream) -> back to the device (`into`, default x itself) chunk by chunk."""
+        src = xin
+        dst = xs if into is not None else xin
         done = torch.cuda.Event()
         done.record(main_stream)
         side.wait_event(done)
+        tgt = up if into is not None else main_stream
         ev = None
         for lo, hi in cuts:
             with torch.cuda.stream(side):
-                xh[lo:hi].copy_(xin[lo:hi], non_blocking=True)          # result -> host
+                xh[lo:hi].copy_(src[lo:hi], non_blocking=True)          # result -> host
                 ev = torch.cuda.Event()
                 ev.record(side)
-            main_stream.wait_event(ev)
-            xin[lo:hi].copy_(xh[lo:hi], non_blocking=True)              # host -> next step's input
-        return ev                                                       # the last read-back chunk has left the device
+            tgt.wait_event(ev)
+            with torch.cuda.stream(tgt):
+                dst[lo:hi].copy_(xh[lo:hi], non_blocking=True)          # host -> (staging for) the next step's input
+        flight['down'] = ev                                             # the last read-back chunk has left the device
+        if into is not None:
+            flight['up'] = torch.cuda.Event()
+            flight['up'].record(up)
+        return ev
 
     def e2e_steps(n):
         pending, sink = None, 0.0
         st.input.copy_(x_host, non_blocking=True)
+        if not canvas:
+            st.optimizer.after_advance = lambda x: x_round_trip(x, into=x_stage)
         for k in range(n):
             if canvas:
                 _, tr = st.step()
                 x_round_trip()
                 sink += float(tr['loss'])
                 continue
-            # x (on the critical path: the next step needs it back) gets the read-back engine first, the iterate image
-            # follows and overlaps the next iteration
+            if flight['up'] is not None:
+                main_stream.wait_event(flight['up'])
+                st.input.copy_(x_stage, non_blocking=True)              # this step's input, as uploaded from the host
             handle = st.step_async(download=False)
-            handle.download(after=x_round_trip())
+            handle.download(after=flight['down'])                      # x first on the read-back engine, then the image
             if pending is not None:
                 img, tr = pending.result()
                 sink += float(tr['loss']) + float(img[0, 0, 0])
@@ -686,6 +702,10 @@ def main():
         if pending is not None:
             img, tr = pending.result()
             sink += float(tr['loss']) + float(img[0, 0, 0])
+        if not canvas:
+            st.optimizer.after_advance = None
+        flight['up'] = flight['down'] = None
+        torch.cuda.synchronize()
         return sink
 
     e2e_steps(2)
@@ -710,7 +730,7 @@ def main():
                'd2h_bytes_per_step': 2 * nbytes + 8 * 560,
                'pcie_gb_per_s_per_gpu': (3 * nbytes + 8 * 560) * args.steps / (ms_e2e / 1000.0) / 1e9,
                'pinned_buffers_numa_node': numa,
-               'note': 'StyleTransfer.step_async(): every step the new x is read back to pinned host memory and the next step input is uploaded from that host buffer (4-chunk pipeline over both copy engines); iterate image (HxWx3 fp32) + trace block read back every step, the image copy overlapping the next iteration'}
+               'note': 'StyleTransfer.step_async(): every step the new x is read back to pinned host memory as soon as L-BFGS has fixed it (start of the step) and the next step input is uploaded from that host buffer into a staging tensor, both overlapping the evaluation; iterate image (HxWx3 fp32) + trace block read back every step, the image copy overlapping the next iteration'}
 
     # ---- per-category device time (CUDA events on the launch stream) for the rooflines
     cats = profile_categories(eng, lambda: st.step(fetch=False), min(args.steps, 10))

@@ -79,6 +79,9 @@ class LBFGSOptimizer:
         self.n_corr = n_corr
         self.loss = None
         self.grad = None
+        # optional hook, called with x right after it has been advanced (and before the objective is evaluated there):
+        # lets a caller start moving the new iterate -- e.g. to the host -- while the evaluation runs
+        self.after_advance = None
         self._eng = utils.default_engine()
         self._h = None
         self._n = 0
@@ -109,6 +112,8 @@ class LBFGSOptimizer:
         if self.loss is None:
             self.loss, self.grad = self.opfunc(self.x)
         self._call('st2_lbfgs_advance', _p(self.x), _p(self.grad), float(self.step_size))
+        if self.after_advance is not None:
+            self.after_advance(self.x)          # the new iterate is final here: the evaluation below only reads it
         loss, grad = self.opfunc(self.x)
         if grad.data_ptr() == self.grad.data_ptr():
             raise RuntimeError('opfunc must hand out a fresh gradient buffer (the optimizer owns the previous one)')
