@@ -39,27 +39,34 @@ for r in rows[2:]:
                      'dram_read': to_bytes(r[ir], units[ir]), 'dram_write': to_bytes(r[iw], units[iw]),
                      'us_under_ncu': to_us(r[it], units[it]),
                      'tensor_pipe_pct': float(r[itp]) if itp is not None and r[itp] else None})
-offset = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-assert len(launches) >= 30, 'expected the 30 tensor-core conv launches of one iteration, got %d' % len(launches)
-launches = launches[:30]
+# Round 2: conv1_1's style gradient is folded into its data-gradient weights, so an iteration has 29 tensor-core conv
+# launches: 12 forward 3x3 (conv1_2 .. conv5_1), 4 style-gradient 1x1 contractions (conv2_1 .. conv5_1), 12
+# data-gradient 3x3 (conv5_1 .. conv1_2) and the dual-source conv1_1 data gradient (tc_conv_ws_kernel<16, 2>), which
+# ends the cycle.  The capture may start anywhere: the cycle is located by that last kernel.
+CYCLE = 29
+ends = [i for i, l in enumerate(launches) if 'tc_conv_ws_kernel<16, 2' in l['kernel']]
+start = next((e + 1 for e in ends if e + 1 + CYCLE <= len(launches)), None)
+assert start is not None, 'no complete iteration (29 launches after a tc_conv_ws_kernel<16, 2>) in the capture'
+launches = launches[start:start + CYCLE]
+assert 'tc_conv_ws_kernel<16, 2' in launches[-1]['kernel'], 'cycle misaligned'
 NAMES = ['conv1_2', 'conv2_1', 'conv2_2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv3_4', 'conv4_1', 'conv4_2', 'conv4_3',
          'conv4_4', 'conv5_1']
 conv, style, first = [], [], []
-for i, l in enumerate(launches):
-    pos = (i + offset) % 30
+for pos, l in enumerate(launches):
     if pos < 12:
         l['what'] = NAMES[pos] + ' fwd'; conv.append(l)
-    elif pos < 17:
-        l['what'] = 'style grad %d' % (pos - 12); style.append(l)
-    elif pos < 29:
-        l['what'] = NAMES[28 - pos] + ' dgrad'; conv.append(l)
+    elif pos < 16:
+        l['what'] = 'style grad %d (%s)' % (pos - 11, ['conv2_1', 'conv3_1', 'conv4_1', 'conv5_1'][pos - 12]); style.append(l)
+    elif pos < 28:
+        l['what'] = NAMES[27 - pos] + ' dgrad'; conv.append(l)
     else:
-        l['what'] = 'conv1_1 dgrad'; first.append(l)
+        l['what'] = 'conv1_1 dgrad + folded style gradient (dual source)'; first.append(l)
 assert len(conv) == 24
 tot = sum(l['dram_read'] + l['dram_write'] for l in conv)
 print(json.dumps({
-    'source': sys.argv[1], 'what': 'ncu --set full, one L-BFGS iteration at 1024x1024, tc_conv_kernel launches',
+    'source': sys.argv[1], 'what': 'ncu --set full, one L-BFGS iteration at 1024x1024, tensor-core conv launches',
     'conv3x3_launches': 24, 'conv3x3_dram_bytes_per_iteration': tot, 'conv3x3_dram_bytes_per_launch': tot / 24,
+    'conv3x3_us_under_ncu': sum(l['us_under_ncu'] for l in conv),
     'conv3x3_tensor_pipe_pct_time_weighted': sum((l['tensor_pipe_pct'] or 0) * l['us_under_ncu'] for l in conv) /
     sum(l['us_under_ncu'] for l in conv),
     'style_grad_dram_bytes_per_iteration': sum(l['dram_read'] + l['dram_write'] for l in style),

@@ -172,7 +172,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
                                           const bool have_inj, const bool have_s, const float cc, const float sc,
                                           const float dc, const float out_scale, const bool want_ss, float& ss,
                                           __half* __restrict__ out_c, const int sw = 0, const bool valid = true,
-                                          const long long pix_stride = 0, const PoolOut po = PoolOut{nullptr, 0, false}) {
+                                          const long long pix_stride = 0, const PoolOut po = PoolOut{nullptr, 0, false},
+                                          const uint32_t* r2 = nullptr) {
   // Called by ALL lanes of the warp (shuffles inside); `valid` = this lane's pixel exists.  pix_stride = elements
   // between horizontally adjacent pixels of the output (cout).
   // out_c: where this chunk's four 16-byte pieces go.  sw = 0: consecutive (global memory).  sw != 0: out_c is
@@ -231,6 +232,12 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
           }
         }
       }
+    }
+    if (r2 != nullptr) {
+      // the style gradient D' F of the same pixels, contracted by this kernel into a second accumulator (fp32):
+      // it enters below the ReLU mask like the other loss diffs
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(sc, __uint_as_float(r2[j]), v[j]);
     }
   } else {
 #pragma unroll
@@ -521,17 +528,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // both shared memories, so per SM the operand traffic from shared memory drops from (128 + BN) to
 // (128 + BN / 2) rows per K step -- the single-CTA kernel at N = 256 is at ~96 B/clk of the 128 B/clk shared
 // memory port.  The pair tile is 16 rows x 16 pixels; CTA rank r owns rows 8r .. 8r+7 of it.
-template <int BN, bool HALO>
+// SFUSE (BN = 128 data gradient above a 128-channel style layer, i.e. conv2_2's above conv2_1): after the 9 x 2 K blocks
+// of the convolution every tile gets ONE more pipeline stage -- the tile's own 256 x 128 activations F of the blob below
+// (tmap_f, centre tap) against the scaled Gram difference D' (tmap_d, 128 x 128) -- into a second accumulator:
+// the style gradient D' F, which the epilogue adds under the mask with the device coefficient.  That replaces a 1 x 1
+// contraction launch, its 67 MB fp16 output at 1024^2 and the read of that output in this epilogue.
+template <int BN, bool HALO, bool SFUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_d,
                 const ConvGeom g, const float* __restrict__ bias, const __half* __restrict__ act,
                 __half* __restrict__ out, const int epi, const TcInject inj) {
+  static_assert(!SFUSE || BN == 128, "style fusion: 128-channel layers only (TMEM holds 4 x 128 columns)");
   constexpr int KB = (BN == 256) ? 1 : 2;                      // K blocks per stage
   constexpr int kABlock = BM * BK * 2;                         // 16 KB
   constexpr int kBBlock = (BN / 2) * BK * 2;                   // this CTA's half of the weight tile
   constexpr int kABytes = KB * kABlock, kBBytes = KB * kBBlock;
   constexpr int kStages = (BN == 256) ? 6 : 4;
-  constexpr int kTmemCols = 2 * BN;
+  constexpr int kTmemCols = SFUSE ? 4 * BN : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -548,7 +562,10 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   if (HALO) halo_push_prologue(g.halo);
 
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); }
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b);
+    if (SFUSE) { tc::prefetch_tmap(&tmap_f); tc::prefetch_tmap(&tmap_d); }
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 8); }
@@ -594,6 +611,22 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (SFUSE) {
+        // the style stage: this CTA's 128 pixels of F (both 64-channel blocks) and its half of D'
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0 && tc::elect_one())
+          tc::mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)KB * (kABlock + kBBlock));
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+          if (tc::elect_one()) {
+            tc::tma_load_3d_2sm(smem_a + stage * kABytes + j * kABlock, &tmap_f, &full_bar[stage], j * BK, w0, h0 + g.hoff);
+            tc::tma_load_2d_2sm(smem_b + stage * kBBytes + j * kBBlock, &tmap_d, &full_bar[stage], j * BK,
+                                nb * BN + (int)rank * (BN / 2));
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader only) ================================
@@ -623,6 +656,23 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                  b_desc + (uint64_t)(j * (kBBlock >> 4) + 2 * k), idesc, (it | j | k) != 0);
             }
           }
+          tc::umma_commit_2sm(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (SFUSE) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kABytes >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kBBytes >> 4));
+#pragma unroll
+          for (int j = 0; j < KB; ++j)
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_f16_2sm(d_tmem + 2 * BN, a_desc + (uint64_t)(j * (kABlock >> 4) + 2 * k),
+                               b_desc + (uint64_t)(j * (kBBlock >> 4) + 2 * k), idesc, (j | k) != 0);
           tc::umma_commit_2sm(&empty_bar[stage]);
         }
         __syncwarp();
@@ -684,12 +734,14 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t r[32];
+          uint32_t r2[SFUSE ? 32 : 1];
           tc::tmem_ld_32x32(t_row + c * 32, r);
+          if (SFUSE) tc::tmem_ld_32x32(t_row + 2 * BN + c * 32, reinterpret_cast<uint32_t(&)[32]>(r2));
           tc::tmem_ld_wait();
           epi_chunk(r, epi, bias + nb * BN + c * 32, pa[PF ? c : 0], ps[PF ? c : 0],
                     (valid && have_inj && inj.fc != nullptr) ? inj.fc + obase + c * 32 : nullptr, have_inj, have_s, cc, sc, dc,
                     1.f, false, ss, out + obase + c * 32, 0, valid, g.cout,
-                    PoolOut{do_pool ? pool_px + c * 32 : nullptr, pool_vert, pool_writer});
+                    PoolOut{do_pool ? pool_px + c * 32 : nullptr, pool_vert, pool_writer}, SFUSE ? r2 : nullptr);
         }
       }
 #pragma unroll 1
@@ -1277,6 +1329,8 @@ struct TcConvPlan {
   CUtensorMap tmap_a, tmap_b;
   CUtensorMap tmap_a2;          // dual-source plans only (tc_conv_dual_plan_create)
   bool dual = false;
+  CUtensorMap tmap_f, tmap_d;   // style fusion (tc_conv_set_style_fuse): activations of the blob below, scaled Gram difference
+  bool sfuse = false;
   ConvGeom g;
   int bn;
   int ws_kb;        // > 0: weight-stationary halo-reuse kernel with this many 64-channel K blocks
@@ -1479,17 +1533,27 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   return 0;
 }
 
-template <int BN>
+template <int BN, bool SFUSE = false>
 static int launch_pair(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                        const TcInject& inj) {
   constexpr int smem = PairCfg<BN>::kSmemBytes;
   int pairs = ctx->sm_count / 2;
   if (pairs > p->g.total_tiles) pairs = p->g.total_tiles;
   p->g.dbg = ctx->debug_flags;
-  if (p->g.rot)
-    tc_conv2_kernel<BN, true><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
-  else
-    tc_conv2_kernel<BN, false><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
+  if (SFUSE) {
+    if (p->g.rot)
+      tc_conv2_kernel<128, true, true><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_f, p->tmap_d,
+                                                                                      p->g, bias, act, out, epi, inj);
+    else
+      tc_conv2_kernel<128, false, true><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_f, p->tmap_d,
+                                                                                       p->g, bias, act, out, epi, inj);
+  } else if (p->g.rot) {
+    tc_conv2_kernel<BN, true, false><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_a, p->tmap_b,
+                                                                                    p->g, bias, act, out, epi, inj);
+  } else {
+    tc_conv2_kernel<BN, false, false><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_a, p->tmap_b,
+                                                                                     p->g, bias, act, out, epi, inj);
+  }
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1517,13 +1581,33 @@ static void set_halo(TcConvPlan* p, const HaloArgs* halo) {
 
 bool tc_conv_supports_halo(const TcConvPlan* p) { return p != nullptr && !(p->ws_kb && p->pair); }
 
+bool tc_conv_supports_style_fuse(const TcConvPlan* p) {
+  return p != nullptr && p->pair && !p->ws_kb && p->bn == 128 && p->g.cout == 128 && p->g.taps == 9;
+}
+
+int tc_conv_set_style_fuse(st2_ctx* ctx, TcConvPlan* p, const __half* act_below, const __half* d_scaled) {
+  if (!tc_conv_supports_style_fuse(p)) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_set_style_fuse: wrong kernel");
+  const ConvGeom& g = p->g;
+  cuuint64_t dims[3] = {(cuuint64_t)g.cout, (cuuint64_t)g.W, (cuuint64_t)(g.H + 2 * g.hoff)};
+  cuuint64_t strides[2] = {(cuuint64_t)g.cout * 2, (cuuint64_t)g.W * g.cout * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH};
+  int rc = st2_encode_tmap(ctx, &p->tmap_f, act_below, 3, dims, strides, box);
+  if (rc) return rc;
+  cuuint64_t dd[2] = {(cuuint64_t)g.cout, (cuuint64_t)g.cout};
+  cuuint64_t ds[1] = {(cuuint64_t)g.cout * 2};
+  cuuint32_t db[2] = {(cuuint32_t)BK, (cuuint32_t)(p->bn / 2)};
+  if ((rc = st2_encode_tmap(ctx, &p->tmap_d, d_scaled, 2, dd, ds, db))) return rc;
+  p->sfuse = true;
+  return 0;
+}
+
 
 int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* dual_coef, const HaloArgs* halo) {
   if (!p || p->bn != 16 || (p->dual != (dual_coef != nullptr)))
     return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
   set_halo(p, halo);
   TcInject inj;
-  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = dual_coef; inj.pool = nullptr; inj.pool_wp = 0;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = dual_coef; inj.pool = nullptr; inj.pool_wp = 0; inj.sfuse = 0;
   if (p->dual) return launch_ws<16, 2>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
   return launch_ws<16, 1>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
 }
@@ -1570,7 +1654,7 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
   set_halo(p, halo);
   if (epi == EPI_MASK && !act) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: act required");
   TcInject inj;
-  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr; inj.pool = nullptr; inj.pool_wp = 0;
+  inj.fc = nullptr; inj.sraw = nullptr; inj.coef = nullptr; inj.pool = nullptr; inj.pool_wp = 0; inj.sfuse = 0;
   if (pooled) *pooled = false;
   if (inj_in) {
     if (epi != EPI_MASK && (inj_in->fc || inj_in->sraw || inj_in->coef))
@@ -1592,8 +1676,12 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
     if (p->ws_kb == 1 && p->bn == 16) return launch_ws<16, 1>(ctx, p, bias, act, out, EPI_RAW, inj);
     return st2_fail(ctx, ST2_ERR_STATE, "tc_conv: no weight-stationary kernel for this shape");
   }
-  if (p->pair && out_scale == 1.f && sumsq == nullptr)
+  if (inj.sfuse && !(p->pair && !p->ws_kb && p->bn == 128 && p->sfuse && epi == EPI_MASK && inj.coef != nullptr))
+    return st2_fail(ctx, ST2_ERR_STATE, "tc_conv: style fusion needs the 128-wide CTA-pair kernel with its maps set");
+  if (p->pair && out_scale == 1.f && sumsq == nullptr) {
+    if (inj.sfuse) return launch_pair<128, true>(ctx, p, bias, act, out, epi, inj);
     return p->bn == 256 ? launch_pair<256>(ctx, p, bias, act, out, epi, inj) : launch_pair<128>(ctx, p, bias, act, out, epi, inj);
+  }
   switch (p->bn) {
     case 256: return launch_bn<256>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
     case 128: return launch_bn<128>(ctx, p, bias, act, out, epi, out_scale, sumsq, inj);
@@ -1627,19 +1715,18 @@ static St2SmemReg g_smem_conv_tc({
 #define SM WsCfg<16, 2>::kSmemBytes
     ST2_BOTH(tc_conv_ws_kernel, 16, 2),
 #undef SM
-#define SM PairCfg<256>::kSmemBytes
-    ST2_BOTH(tc_conv2_kernel, 256),
-#undef SM
-#define SM PairCfg<128>::kSmemBytes
-    ST2_BOTH(tc_conv2_kernel, 128),
-#undef SM
+    {ST2_KFN(tc_conv2_kernel<256, false, false>), PairCfg<256>::kSmemBytes}, {ST2_KFN(tc_conv2_kernel<256, true, false>), PairCfg<256>::kSmemBytes},
+    {ST2_KFN(tc_conv2_kernel<128, false, false>), PairCfg<128>::kSmemBytes}, {ST2_KFN(tc_conv2_kernel<128, true, false>), PairCfg<128>::kSmemBytes},
+    {ST2_KFN(tc_conv2_kernel<128, false, true>), PairCfg<128>::kSmemBytes}, {ST2_KFN(tc_conv2_kernel<128, true, true>), PairCfg<128>::kSmemBytes},
     {ST2_KFN(tc_conv_wsp_kernel<1>), WspCfg<1>::kSmemBytes}, {ST2_KFN(tc_conv_wsp_kernel<2>), WspCfg<2>::kSmemBytes}});
 #undef ST2_BOTH
 #define ST2_BOTH(K, ...) ST2_KFN(K<__VA_ARGS__, false>), ST2_KFN(K<__VA_ARGS__, true>)
 static St2KernelReg g_reg_conv_tc({ST2_BOTH(tc_conv_kernel, 256), ST2_BOTH(tc_conv_kernel, 128), ST2_BOTH(tc_conv_kernel, 64),
                                       ST2_BOTH(tc_conv_ws_kernel, 64, 1), ST2_BOTH(tc_conv_ws_kernel, 128, 1),
                                       ST2_BOTH(tc_conv_ws_kernel, 64, 2), ST2_BOTH(tc_conv_ws_kernel, 16, 1),
-                                      ST2_BOTH(tc_conv_ws_kernel, 16, 2), ST2_BOTH(tc_conv2_kernel, 256),
-                                      ST2_BOTH(tc_conv2_kernel, 128),
+                                      ST2_BOTH(tc_conv_ws_kernel, 16, 2),
+                                      ST2_KFN(tc_conv2_kernel<256, false, false>), ST2_KFN(tc_conv2_kernel<256, true, false>),
+                                      ST2_KFN(tc_conv2_kernel<128, false, false>), ST2_KFN(tc_conv2_kernel<128, true, false>),
+                                      ST2_KFN(tc_conv2_kernel<128, false, true>), ST2_KFN(tc_conv2_kernel<128, true, true>),
                                       ST2_KFN(tc_conv_wsp_kernel<1>), ST2_KFN(tc_conv_wsp_kernel<2>)});
 #undef ST2_BOTH

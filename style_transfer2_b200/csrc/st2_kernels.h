@@ -99,12 +99,18 @@ void tc_conv_plan_destroy(TcConvPlan* p);
 // the blob below enter under its ReLU mask in the same pass (fc / sraw nullable; coef: 3 device doubles)
 // pool / pool_wp (EPI_BIAS_RELU only): also write the 2x2/2 ceil-mode max-pool of the output (NHWC, pool_wp pixels
 // per row) from the same epilogue; *pooled (tc_conv_launch) tells whether the launched kernel did it
-struct TcInject { const __half* fc; const __half* sraw; const double* coef; __half* pool; int pool_wp; };
+// sfuse (EPI_MASK, CTA-pair kernel with N = 128 only, after tc_conv_set_style_fuse): the style gradient D' F of the blob
+// below is contracted by the same kernel into a second accumulator and added with coef[1] -- sraw must then be nullptr
+struct TcInject { const __half* fc; const __half* sraw; const double* coef; __half* pool; int pool_wp; int sfuse; };
 int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half* act, __half* out, int epi,
                    float out_scale, double* sumsq, const TcInject* inj = nullptr, bool* pooled = nullptr,
                    const HaloArgs* halo = nullptr);
 // does the kernel this plan launches carry the in-kernel halo push / wait?
 bool tc_conv_supports_halo(const TcConvPlan* p);
+// style fusion into the data-gradient convolution ABOVE a 128-channel style layer: act_below = that layer's activations
+// (same geometry as this convolution's output; on strips the padded tensor), d_scaled = C x C fp16 (rewritten per evaluation)
+bool tc_conv_supports_style_fuse(const TcConvPlan* p);
+int tc_conv_set_style_fuse(st2_ctx* ctx, TcConvPlan* p, const __half* act_below, const __half* d_scaled);
 // conv1_1 data gradient on the tensor cores: plan made with cin = 64, cout = 16 (the 3 image planes padded),
 // weights [16][tap'][64] fp16; writes fp32 NCHW (3 dense planes of H x W)
 // dual plan (tc_conv_dual_plan_create): gx = convT_W(grad) + dual_coef[1] * convT_W'(act) in one launch

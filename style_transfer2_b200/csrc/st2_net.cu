@@ -163,6 +163,27 @@ style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, cons
   if ((threadIdx.x & 31) == 0) atomicAdd(raw_sum, tot * (double)ds * (double)ds);
 }
 
+// sum_p |D' F_p|^2 = <D'^T D', F^T F> for a style layer whose gradient is never materialised (see above; ds is read
+// from sb[SB_S_DSCALE], written by style_scale_kernel just before).  gsum_local: this strip's un-normalised Gram sum,
+// or nullptr for the whole canvas (F^T F = (D + A) C HW).  One (j, k) pair per thread.
+__global__ void __launch_bounds__(256)
+style_rawsq_kernel(const float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ gsum_local, int C,
+                   double n_total, const double* sb, double* raw_sum) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double tot = 0.0;
+  if (idx < (long long)C * C) {
+    const int j = (int)(idx / C), k = (int)(idx % C);
+    double e = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < C; ++i) e += (double)__ldg(D + (long long)i * C + j) * (double)__ldg(D + (long long)i * C + k);
+    tot = gsum_local != nullptr ? e * (double)gsum_local[idx]
+                                : e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0)) * n_total;
+  }
+  tot = warp_sum_d(tot);
+  const double ds = sb[SB_S_DSCALE];
+  if ((threadIdx.x & 31) == 0 && tot != 0.0) atomicAdd(raw_sum, tot * ds * ds);
+}
+
 // conv1_1 data-gradient weights [16][9][64] -> the gradient-channel half of the dual pack [16][9][128]
 __global__ void dual_pack_kernel(const __half* __restrict__ wbwd, __half* __restrict__ wdual) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,6 +271,7 @@ struct Blob {
   TcConvPlan* tc_style = nullptr;
   TcConvPlan* tc_sfold = nullptr;  // conv1_1: data gradient with two sources (gradient + activations), dual weights
   __half* wfold = nullptr;         // conv1_1: [16][9][128] fp16: W for the gradient channels | W' = W D for the activations
+  bool dfuse_set = false;          // the tensor maps of the style fusion are installed in the plan of the layer above
   TcGramPlan* tc_gram = nullptr;
   TcFirstPlan* tc_first = nullptr; // conv1_1 only
   long long n() const { return (long long)C * H * W; }
@@ -259,6 +281,7 @@ struct Blob {
 struct Inject {
   bool on = false;
   bool fold = false;          // conv1_1: the style term is applied by a second data-gradient pass (style_fold_kernel)
+  bool dfuse = false;         // the data-gradient kernel of the layer ABOVE contracts D' F itself (TcInject::sfuse)
   const void* fc = nullptr;
   const void* sraw = nullptr;
   const double* coef = nullptr;
@@ -410,7 +433,8 @@ struct st2_plan {
   unsigned long long epoch[kSlots] = {};
   float* xp = nullptr;                               // padded copy of x: 3 x (H + 2) x W
   float* gram_red = nullptr;                         // strip Gram sums, fp32, all-reduced by the caller
-  float* gram_local1 = nullptr;                      // conv1_1's strip Gram sum as it was before the all-reduce (style fold)
+  float* gram_local[ST2_NUM_BLOBS] = {};             // strip Gram sums as they were before the all-reduce (conv1_1 / conv2_1:
+                                                     // their style gradient is never materialised, see fold_eligible / dfuse_eligible)
   long long gram_red_off[ST2_NUM_BLOBS] = {};
   long long gram_red_used = 0;
   double* red = nullptr;                             // 3 partial sums per blob, all-reduced by the caller
@@ -566,7 +590,7 @@ static int forward_impl(st2_plan* pl, const float* x, int top) {
       } else {
         // a max-pool right above this convolution is computed by the same epilogue when the kernel supports it
         TcInject ti;
-        ti.fc = nullptr; ti.sraw = nullptr; ti.coef = nullptr; ti.pool = nullptr; ti.pool_wp = 0;
+        ti.fc = nullptr; ti.sraw = nullptr; ti.coef = nullptr; ti.pool = nullptr; ti.pool_wp = 0; ti.sfuse = 0;
         if (i + 1 <= top && g_blobs[i + 1].kind == KIND_POOL) { ti.pool = (__half*)pl->b[i + 1].act; ti.pool_wp = pl->b[i + 1].W; }
         // row strips: this kernel also carries the exchange of its input's boundary rows (or the exchange kernel ran
         // after the producer, see the end of the loop body)
@@ -654,6 +678,7 @@ static int backward_impl(st2_plan* pl, int top, const Inject* inj, float* grad_o
         TcInject ti;
         ti.fc = (const __half*)inj[i - 1].fc; ti.sraw = (const __half*)inj[i - 1].sraw; ti.coef = inj[i - 1].coef;
         ti.pool = nullptr; ti.pool_wp = 0;
+        ti.sfuse = inj[i - 1].dfuse ? 1 : 0;      // the style gradient of the blob below is contracted by this kernel
         rc = tc_conv_launch(ctx, cur.tc_bwd, nullptr, (const __half*)below.act, (__half*)below.grad, EPI_MASK, 1.f,
                             nullptr, &ti, nullptr, hap);
         fused_inj = true;
@@ -738,6 +763,14 @@ static bool fold_eligible(const st2_plan* pl, int b) {
   return b == 1 && pl->prec == ST2_PREC_FP16 && !pl->ctx->knobs.no_style_fuse && pl->b[b].tc_bwd != nullptr &&
          (!pl->strip || pl->strip_fold);
 }
+// conv2_1 (128 channels): its style gradient D' F is contracted inside the data-gradient kernel of conv2_2, the layer
+// above, as one extra pipeline stage per tile into a second accumulator (TcInject::sfuse) -- when that kernel is the
+// 128-wide CTA-pair kernel and the backward pass starts above conv2_1.  grad(conv2_1) holds the same values either
+// way, so strips may decide differently.
+static bool dfuse_eligible(const st2_plan* pl, int b, int want_grad) {
+  return b == 4 && want_grad && pl->prec == ST2_PREC_FP16 && !pl->ctx->knobs.no_style_fuse && pl->eval_top >= b + 1 &&
+         !pl->ctx->knobs.no_fused_inject && tc_conv_supports_style_fuse(pl->b[b + 1].tc_bwd);
+}
 
 // The objective (worker.py:231-301) in four phases.  On a whole-canvas plan st2_eval runs them back to
 // back.  On a row strip the caller all-reduces (sum) one small block between consecutive phases:
@@ -796,7 +829,7 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
     if (s_on) {
       const size_t e = (b == 0) ? sizeof(float) : pl->esz;
       if ((rc = ensure(ctx, (void**)&B.D, sizeof(float) * B.C * B.C))) return rc;
-      if (!fold_eligible(pl, b) && (rc = ensure(ctx, &B.sraw, e * B.n()))) return rc;
+      if (!fold_eligible(pl, b) && !dfuse_eligible(pl, b, want_grad) && (rc = ensure(ctx, &B.sraw, e * B.n()))) return rc;
       ProfScope ps(ctx, 3);
       if (pl->strip) {
         pl->gram_red_off[b] = pl->gram_red_used;
@@ -828,9 +861,15 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
     ProfScope ps(ctx, 10);
     if ((rc = tc_gram_finalize_all(ctx, n_gram, gp, gA, gD, gS, pl->strip ? 1 : 0))) return rc;
   }
-  if (pl->strip && host_w_on(pl->b[1].sw) && fold_eligible(pl, 1))
-    ST2_CUDA(ctx, cudaMemcpyAsync(pl->gram_local1, pl->gram_red + pl->gram_red_off[1], sizeof(float) * 64 * 64,
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
+  if (pl->strip) {
+    for (int b = 1; b <= 4; b += 3) {            // conv1_1 and conv2_1
+      if (!host_w_on(pl->b[b].sw) || !(b == 1 ? fold_eligible(pl, b) : dfuse_eligible(pl, b, want_grad))) continue;
+      const size_t bytes = sizeof(float) * pl->b[b].C * pl->b[b].C;
+      if ((rc = ensure(ctx, (void**)&pl->gram_local[b], bytes))) return rc;
+      ST2_CUDA(ctx, cudaMemcpyAsync(pl->gram_local[b], pl->gram_red + pl->gram_red_off[b], bytes, cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
+    }
+  }
   pl->eval_phase = 1;
   return 0;
 }
@@ -867,11 +906,27 @@ static int eval_mid_impl(st2_plan* pl) {
                                                         (const __half*)(pl->strip ? B.act_pad : B.act), B.wfold, B.H, B.W,
                                                         &B.tc_sfold, pl->strip ? 1 : 0)))
         return rc;
-      style_fold_kernel<<<32, 128, 0, ctx->stream>>>(B.D, B.gram_target, pl->strip ? pl->gram_local1 : nullptr,
+      style_fold_kernel<<<32, 128, 0, ctx->stream>>>(B.D, B.gram_target, pl->strip ? pl->gram_local[1] : nullptr,
                                                      ctx->w_oihw[0], B.wfold, B.n_total(), sb, raw_sum);
       ST2_LAUNCH_CHECK(ctx);
       pl->inj[b].sraw = nullptr;
       pl->inj[b].fold = true;
+      continue;
+    }
+    if (dfuse_eligible(pl, b, want_grad)) {
+      if ((rc = ensure(ctx, (void**)&B.Dh, sizeof(__half) * B.C * B.C))) return rc;
+      TcConvPlan* above = pl->b[b + 1].tc_bwd;
+      if (!B.dfuse_set) {
+        if ((rc = tc_conv_set_style_fuse(ctx, above, (const __half*)(pl->strip ? B.act_pad : B.act), B.Dh))) return rc;
+        B.dfuse_set = true;
+      }
+      style_scale_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(B.D, B.Dh, B.C, sb);
+      ST2_LAUNCH_CHECK(ctx);
+      style_rawsq_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(
+          B.D, B.gram_target, pl->strip ? pl->gram_local[b] : nullptr, B.C, B.n_total(), sb, raw_sum);
+      ST2_LAUNCH_CHECK(ctx);
+      pl->inj[b].sraw = nullptr;
+      pl->inj[b].dfuse = true;
       continue;
     }
     if (want_grad) {
@@ -1114,7 +1169,6 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
     long long gtot = 0;
     for (int i = 0; i < ST2_NUM_BLOBS; ++i) gtot += (long long)g_blobs[i].channels * g_blobs[i].channels;
     ST2_CUDA(ctx, cudaMalloc(&pl->gram_red, sizeof(float) * gtot));
-    ST2_CUDA(ctx, cudaMalloc(&pl->gram_local1, sizeof(float) * 64 * 64));
   }
   int h = H, w = W, hg = H_total;
   for (int i = 0; i < ST2_NUM_BLOBS; ++i) {
@@ -1257,7 +1311,8 @@ void st2_plan_destroy(st2_plan* pl) {
     tc_gram_plan_destroy(B.tc_gram);
     tc_first_plan_destroy(B.tc_first);
   }
-  cudaFree(pl->slab); cudaFree(pl->red); cudaFree(pl->gram_red); cudaFree(pl->gram_local1);
+  cudaFree(pl->slab); cudaFree(pl->red); cudaFree(pl->gram_red);
+  for (int i = 0; i < ST2_NUM_BLOBS; ++i) cudaFree(pl->gram_local[i]);
   cudaFree(pl->scal); cudaFree(pl->gram_acc); cudaFree(pl->bwd); cudaFree(pl->part); cudaFree(pl->part_counter);
   delete pl;
 }
@@ -1481,5 +1536,5 @@ int st2_gram_nchw(st2_ctx* ctx, const float* x, int C, long long HW, float* out)
 }  // extern "C"
 
 static St2KernelReg g_reg_net({ST2_KFN(halo_exchange_kernel), ST2_KFN(pack_x_kernel),
-                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(style_fold_kernel), ST2_KFN(dual_pack_kernel), ST2_KFN(scatter_sums_kernel),
+                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(style_fold_kernel), ST2_KFN(style_rawsq_kernel), ST2_KFN(dual_pack_kernel), ST2_KFN(scatter_sums_kernel),
                                   ST2_KFN(coef_kernel), ST2_KFN(final_kernel), ST2_KFN(pack_weights_kernel)});
