@@ -792,8 +792,16 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 //     descriptors into that patch: start = patch + (r*16 + s) * 128 B, stride between 8-pixel row groups
 //     (SBO) = 2048 B (base_offset stays 0: the swizzle follows absolute address bits, see smem_desc_patch).
 // A traffic drops 4x (36 KB instead of 144 KB); the layer becomes MMA / HBM bound.
-constexpr int kPatchW = 16, kPatchH = 18;
-constexpr int kPatchBytes = kPatchW * kPatchH * 128;          // 36 864 = 36 x 1024
+// Patch = the 16 x 8 pixel tile plus its one-pixel halo: 18 rows x (8 + 2) pixels x 128 B.  The rows of a patch are
+// 10 pixels = 1280 B apart (SBO of the UMMA descriptors); round 1 fetched 16 pixels per row (2048 B, a power of two)
+// of which 6 were never read -- 37 % of the L2 -> shared-memory fill and of the shared-memory write bandwidth the
+// N = 64 layers are bound by.
+#ifndef ST2_PATCH_W
+#define ST2_PATCH_W 10
+#endif
+constexpr int kPatchW = ST2_PATCH_W, kPatchH = 18;
+constexpr int kPatchTx = kPatchW * kPatchH * 128;             // bytes one TMA box delivers (23 040)
+constexpr int kPatchBytes = (kPatchTx + 1023) / 1024 * 1024;  // stage stride: SWIZZLE_128B tiles start 1024-byte aligned
 constexpr int kWsTW = 8, kWsTH = 16;
 
 template <int BN, int KB> struct WsCfg {
@@ -803,8 +811,11 @@ template <int BN, int KB> struct WsCfg {
   // 128-byte stride cap the epilogue at ~1.8 TB/s (measured 76 us for conv1_2's 134 MB with everything else
   // switched off), whole-line bulk stores do not.
   static constexpr bool kTmaStore = (KB == 1 && BN == 64);
-  static constexpr int kStages = kTmaStore ? 3 : (kWBytes <= 73728 ? 4 : 2);
-  static constexpr int kOutBytes = kTmaStore ? 2 * BM * 128 : 0;       // two 16 KB staging tiles
+  static constexpr int kStages = kTmaStore ? 4 : (kWBytes <= 73728 ? 4 : (kWBytes + 3 * kPatchBytes + 1280 <= 232448 ? 3 : 2));
+  // three 16 KB tiles: in the masked (data-gradient) epilogue a tile is first the landing zone of the ReLU-mask
+  // source (a TMA load issued one tile ahead), then -- in place, thread = pixel row -- the output staging tile of
+  // the TMA store; the forward epilogue uses two of them for staging only
+  static constexpr int kOutBytes = kTmaStore ? 3 * BM * 128 : 0;
   static constexpr int kAccStride = BN < 32 ? 32 : BN;                 // TMEM columns per accumulator
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kSmemBytes = kWBytes + kStages * kPatchBytes + kOutBytes + 1024 + 256;
@@ -818,7 +829,7 @@ __device__ __forceinline__ uint64_t smem_desc_patch(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(2048 >> 4) << 32;                            // SBO: next 8-pixel group = next patch row
+  d |= (uint64_t)((kPatchW * 128) >> 4) << 32;                 // SBO: next 8-pixel group = next patch row
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
@@ -828,7 +839,7 @@ template <int BN, int KB, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_a2,
-                  const ConvGeom g, const float* __restrict__ bias,
+                  const __grid_constant__ CUtensorMap tmap_m, const ConvGeom g, const float* __restrict__ bias,
                   const __half* __restrict__ act, __half* __restrict__ out, const int epi, const TcInject inj) {
   using C = WsCfg<BN, KB>;
   // <16, 2>: conv1_1 data gradient from TWO 64-channel tensors (the gradient through tmap_a, conv1_1's activations
@@ -846,7 +857,8 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_full = bars + 2 * C::kStages;
   uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
   uint64_t* w_full = bars + 2 * C::kStages + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 5);
+  uint64_t* m_full = bars + 2 * C::kStages + 5;      // [3] mask-source tiles (TMA-store variant, masked epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // a CTA keeps one N block for its whole life (its weights are resident); pixel tiles are strided
@@ -863,6 +875,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
     tc::mbar_init(w_full, 1);
+    for (int a = 0; a < 3; ++a) tc::mbar_init(&m_full[a], 1);
     tc::fence_mbar_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, C::kTmemCols);
@@ -894,7 +907,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (g.dbg & 4) {
             tc::mbar_arrive(&full_bar[stage]);
           } else {
-            tc::mbar_expect_tx(&full_bar[stage], kPatchBytes);
+            tc::mbar_expect_tx(&full_bar[stage], kPatchTx);
             tc::tma_load_3d(smem_p + stage * kPatchBytes, (DUAL && kb == 1) ? &tmap_a2 : &tmap_a, &full_bar[stage],
                             DUAL ? 0 : kb * BK, w0 - 1, h0 - 1 + g.hoff);
           }
@@ -954,6 +967,16 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const bool have_inj = masked && inj.coef != nullptr;
     const bool have_s = have_inj && inj.sraw != nullptr;
     int local = 0;
+    // TMA-store variant, masked epilogue: the tile of the ReLU-mask source (the 16 x 8 pixels x 64 channels this
+    // tile's outputs belong to) is fetched by TMA into staging buffer (tile % 3) ONE TILE AHEAD, by the same thread
+    // that issues the tile stores -- it knows when the store that last used the buffer has finished reading it.
+    const bool mtma = C::kTmaStore && BN == 64 && masked && !(g.dbg & 1);
+    auto load_mask_tile = [&](const int ptq, const int buf) {
+      const int thq = rot_row<HALO>(g, ptq / g.tiles_w), twq = ptq - (ptq / g.tiles_w) * g.tiles_w;
+      tc::mbar_expect_tx(&m_full[buf], BM * 128);
+      tc::tma_load_3d(smem_o + buf * (BM * 128), &tmap_m, &m_full[buf], nb * BN, twq * kWsTW, thq * kWsTH);
+    };
+    if (mtma && warp == kEpiWarp0 && lane == 0 && pt0 < n_pt) load_mask_tile(pt0, 0);
     for (int pt = pt0; pt < n_pt; pt += pt_step, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -1014,7 +1037,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int hh = th * kWsTH + ew * 4 + (j >> 1), ww = tw * kWsTW + (j & 1) * 4 + (lane >> 3);
             const long long o = ((long long)hh * g.W + ww) * g.cout + (lane & 7) * 8;
             const bool ok = hh < g.H && ww < g.W && !(g.dbg & 1);
-            pa[j >> 2][j & 3] = ok ? __ldg(reinterpret_cast<const uint4*>(act + o)) : make_uint4(0, 0, 0, 0);
+            if (!mtma) pa[j >> 2][j & 3] = ok ? __ldg(reinterpret_cast<const uint4*>(act + o)) : make_uint4(0, 0, 0, 0);
             if (have_s) ps[j >> 2][j & 3] = ok ? __ldg(reinterpret_cast<const uint4*>(inj.sraw + o)) : make_uint4(0, 0, 0, 0);
           }
         }
@@ -1039,10 +1062,21 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc::fence_after_sync();
       const uint32_t t_row = tmem_base + acc * C::kAccStride + ((uint32_t)(ew * 32) << 16);
       if (C::kTmaStore) {
-        // staging tile `acc`: the bulk store issued from it two tiles ago must have finished reading it
-        uint8_t* stg = smem_o + acc * (BM * 128);
-        if (warp == kEpiWarp0 && lane == 0) tc::bulk_wait_read<1>();
-        tc::named_bar_sync(1, 128);
+        // staging tile: the bulk store issued from it two (forward: buffers 0 / 1) or three (masked: 0 / 1 / 2) tiles ago
+        // must have finished reading it
+        const int buf = mtma ? local % 3 : acc;
+        uint8_t* stg = smem_o + buf * (BM * 128);
+        if (warp == kEpiWarp0 && lane == 0) {
+          tc::bulk_wait_read<1>();
+          // ... which also frees the buffer of the tile after this one: fetch its mask source now
+          if (mtma && pt + pt_step < n_pt) load_mask_tile(pt + pt_step, (local + 1) % 3);
+        }
+        if (mtma) {
+          if (lane == 0) tc::mbar_wait(&m_full[buf], (local / 3) & 1);
+          __syncwarp();
+        } else {
+          tc::named_bar_sync(1, 128);
+        }
         __half* srow = reinterpret_cast<__half*>(stg + row * 128);
         const bool do_pool = (epi == EPI_BIAS_RELU) && inj.pool != nullptr;
         __half* const pool_px = do_pool ? inj.pool + ((long long)(h >> 1) * inj.pool_wp + (w >> 1)) * g.cout + (long long)nb * BN
@@ -1051,8 +1085,14 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // re-sort the coalesced pieces: piece j of lane l belongs to staging row (ew*4 + j/2)*8 + (j%2)*4 + l/8,
           // chunk l%8; afterwards every thread reads the eight chunks of its own row
           uint4* sl = reinterpret_cast<uint4*>(stg);
+          if (mtma) {
+            // the mask source of this thread's pixel row, straight from the TMA-written (swizzled) tile
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
+            for (int j = 0; j < 8; ++j) pa[j >> 2][j & 3] = sl[row * 8 + (j ^ (row & 7))];
+            if (have_s) tc::named_bar_sync(1, 128);            // the tile doubles as scratch for the re-sort below
+          }
+#pragma unroll
+          for (int pass = mtma ? 1 : 0; pass < 2; ++pass) {
             if (pass == 1 && !have_s) break;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -1183,7 +1223,7 @@ tc_conv_wsp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
         tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (rank == 0 && tc::elect_one()) tc::mbar_expect_tx(&full_bar[stage], 2u * kPatchBytes);
+        if (rank == 0 && tc::elect_one()) tc::mbar_expect_tx(&full_bar[stage], 2u * kPatchTx);
         if (tc::elect_one())
           tc::tma_load_3d_2sm(smem_p + stage * kPatchBytes, &tmap_a, &full_bar[stage], kb * BK, w0 - 1, h0 - 1 + g.hoff);
         __syncwarp();
@@ -1337,6 +1377,8 @@ struct TcConvPlan {
   bool pair;        // CTA-pair kernel (cta_group::2): tiles_h counts 16-row pair tiles, tmap_b box is BN / 2 rows
   CUtensorMap tmap_o;           // output tile stores of the weight-stationary kernel, encoded on first use
   const void* tmap_o_base = nullptr;
+  CUtensorMap tmap_m;           // mask-source tile loads of its masked epilogue, encoded on first use
+  const void* tmap_m_base = nullptr;
 };
 
 static int get_encoder(st2_ctx* ctx, EncodeTiledFn* fn) {
@@ -1517,6 +1559,15 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
     if (rc) return rc;
     p->tmap_o_base = out;
   }
+  if (WsCfg<BN, KB>::kTmaStore && epi == EPI_MASK && p->tmap_m_base != (const void*)act) {
+    cuuint64_t dims[3] = {(cuuint64_t)p->g.cout, (cuuint64_t)p->g.W, (cuuint64_t)p->g.H};
+    cuuint64_t strides[2] = {(cuuint64_t)p->g.cout * 2, (cuuint64_t)p->g.W * p->g.cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BN, (cuuint32_t)kWsTW, (cuuint32_t)kWsTH};
+    int rc = st2_encode_tmap(ctx, &p->tmap_m, act, 3, dims, strides, box);
+    if (rc) return rc;
+    p->tmap_m_base = act;
+  }
+  const CUtensorMap& tm = (WsCfg<BN, KB>::kTmaStore && epi == EPI_MASK) ? p->tmap_m : p->tmap_a;
   const int nbk = p->g.n_blocks;
   const int n_pt = p->g.tiles_h * p->g.tiles_w;
   int per_nb = ctx->sm_count / nbk;
@@ -1525,10 +1576,10 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   p->g.dbg = ctx->debug_flags;
   if (p->g.rot)
     tc_conv_ws_kernel<BN, KB, true><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
-        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, p->g, bias, act, out, epi, inj);
+        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, tm, p->g, bias, act, out, epi, inj);
   else
     tc_conv_ws_kernel<BN, KB, false><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
-        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, p->g, bias, act, out, epi, inj);
+        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, tm, p->g, bias, act, out, epi, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
