@@ -51,6 +51,7 @@ struct st2_ctx {
   __half* wh_fwd[ST2_NUM_CONVS] = {};
   __half* wh_bwd[ST2_NUM_CONVS] = {};
   __half* wh_first = nullptr;      // conv1_1 forward pack for the sliding-window tensor-core kernel
+  __half* wh_bwd_all = nullptr;    // conv1_1 data-gradient pack of the stencil form: [tap' * 3 + plane (27 of 32)][64]
   void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled entry point
   long long launches = 0;          // kernels launched through this context
   int debug_flags = 0;             // timing experiments only (st2_debug_flags)
@@ -58,7 +59,7 @@ struct st2_ctx {
   // production kernels): read ONCE in st2_ctx_create, never on a launch path
   struct Knobs {
     bool no_fused_inject = false, no_tc_gram = false, no_tc_first = false, no_ws = false, force_pair = false,
-         wsp = false, no_pair = false, no_pool_fusion = false, no_style_fuse = false, no_graph = false, no_inkernel_halo = false;
+         wsp = false, no_pair = false, no_pool_fusion = false, no_style_fuse = false, no_graph = false, no_inkernel_halo = false, no_stencil = false;
     int tc_bn = 0;
     long long pair_min_tiles = -1;
   } knobs;

@@ -1154,6 +1154,188 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+
+// ================================================================================================
+// conv1_1 data gradient in "1x1 + stencil" form.  The convolution maps 64 channels to only 3 image planes, so
+//     gx[q, plane] = sum_tap sum_ch g[q + off(tap), ch] W[plane][tap][ch] = sum_tap T[q + off(tap)][tap * 3 + plane]
+// with T = g W_all a POINTWISE contraction 64 -> 27 (9 taps x 3 planes, N padded to 32): per 16 x 8 pixel tile the
+// 18 x 10 pixel patch (tile + halo) is multiplied ONCE by the 27 x 64 weight matrix -- two M = 128 chunks of patch
+// pixels x 4 K steps = 8 MMAs -- instead of nine shifted 128 x 16 x 64 contractions = 36 MMAs that each re-read their
+// A operand from shared memory (the N = 16 kernel was bound by exactly that: 63 us for 134 MB).  The 27 values of
+// every patch pixel go TMEM -> registers -> shared memory, and each output pixel sums its 9 x 3 neighbours there.
+// DUAL: a second source (conv1_1's activations with the folded style weights W' = W D', st2_net.cu style_fold_kernel)
+// gets its own accumulators; the two are combined with the device coefficient before the stencil.
+constexpr int kStPx = kPatchW * kPatchH;                     // 180 patch pixels
+constexpr int kStN = 32;                                     // 27 outputs per patch pixel, padded
+template <bool DUAL> struct StCfg {
+  static constexpr int kSrc = DUAL ? 2 : 1;
+  static constexpr int kWBytes = kSrc * kStN * 128;          // [source][32 rows][64 ch] fp16
+  static constexpr int kStages = 6;
+  static constexpr int kStageBytes = 2 * BM * 128;           // two M = 128 chunks of 128-byte rows (patch + slack)
+  static constexpr int kUBytes = kStPx * 27 * 4;             // fp32 [180][27]
+  static constexpr int kAccStride = kSrc * 2 * kStN;         // TMEM columns per accumulator set
+  static constexpr int kTmemCols = 2 * kAccStride < 32 ? 32 : 2 * kAccStride;
+  static constexpr int kSmemBytes = ((kWBytes + 1023) / 1024) * 1024 + kStages * kStageBytes +
+                                    ((kUBytes + 1023) / 1024) * 1024 + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "stencil kernel: shared memory");
+};
+
+template <bool DUAL, bool HALO>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_conv_first_stencil_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                             const __grid_constant__ CUtensorMap tmap_b, const ConvGeom g, float* __restrict__ gx,
+                             const double* __restrict__ coef) {
+  using C = StCfg<DUAL>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;                                   // [source][32 rows][128 B], SWIZZLE_128B
+  uint8_t* smem_p = smem + ((C::kWBytes + 1023) / 1024) * 1024;
+  float* smem_u = reinterpret_cast<float*>(smem_p + C::kStages * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_u) + ((C::kUBytes + 1023) / 1024) * 1024);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = bars + 2 * C::kStages + 2;
+  uint64_t* w_full = bars + 2 * C::kStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pt = g.tiles_h * g.tiles_w;
+  if (HALO) halo_push_prologue(g.halo);
+
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); if (DUAL) tc::prefetch_tmap(&tmap_a2); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
+    tc::mbar_init(w_full, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, C::kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(w_full, C::kWBytes);
+      for (int sidx = 0; sidx < C::kSrc; ++sidx)
+        tc::tma_load_2d(smem_w + sidx * (kStN * 128), &tmap_b, w_full, 0, sidx * kStN);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    bool waited = false;
+    for (int pt = blockIdx.x; pt < n_pt; pt += gridDim.x) {
+      const int ths = pt / g.tiles_w, tw = pt - ths * g.tiles_w;
+      waited = halo_ready<HALO>(g, waited, ths);
+      const int th = rot_row<HALO>(g, ths);
+      const int h0 = th * kWsTH, w0 = tw * kWsTW;
+#pragma unroll
+      for (int sidx = 0; sidx < C::kSrc; ++sidx) {
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&full_bar[stage], kPatchTx);
+          tc::tma_load_3d(smem_p + stage * C::kStageBytes, sidx ? &tmap_a2 : &tmap_a, &full_bar[stage], 0, w0 - 1,
+                          h0 - 1 + g.hoff);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    constexpr uint32_t idesc = tc::idesc_f16(BM, kStN, 0, 0);
+    const uint64_t a_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_p));
+    const uint64_t b_desc0 = tc::smem_desc_k_sw128(tc::smem_u32(smem_w));
+    tc::mbar_wait(w_full, 0);
+    tc::fence_after_sync();
+    int stage = 0; uint32_t phase = 0;
+    int local = 0;
+    for (int pt = blockIdx.x; pt < n_pt; pt += gridDim.x, ++local) {
+      const int acc = local & 1;
+      tc::mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int sidx = 0; sidx < C::kSrc; ++sidx) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {                  // patch pixels 0..127 and 128..255 (180.. : slack, unused)
+            const uint32_t d_tmem = tmem_base + acc * C::kAccStride + (sidx * 2 + c) * kStN;
+            const uint64_t a_desc = a_desc0 + (uint64_t)((stage * C::kStageBytes + c * (BM * 128)) >> 4);
+            const uint64_t b_desc = b_desc0 + (uint64_t)((sidx * (kStN * 128)) >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, k != 0);
+          }
+          tc::umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (tc::elect_one()) tc::umma_commit(&tmem_full[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ epilogue ====================================
+    const int ew = warp - kEpiWarp0;
+    const int row = ew * 32 + lane;                    // TMEM lane = patch pixel (chunk 0) / patch pixel - 128 (chunk 1)
+    const int out_r = row / kWsTW, out_c = row % kWsTW; // this thread's output pixel inside the tile
+    const float sc = (DUAL && coef != nullptr) ? (float)coef[1] : 0.f;
+    const long long plane = (long long)g.H * g.W;
+    int local = 0;
+    for (int pt = blockIdx.x; pt < n_pt; pt += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const int ths = pt / g.tiles_w, tw = pt - ths * g.tiles_w;
+      const int th = rot_row<HALO>(g, ths);
+      if (lane == 0) tc::mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+      __syncwarp();
+      tc::fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * C::kAccStride + ((uint32_t)(ew * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        uint32_t r2[DUAL ? 32 : 1];
+        tc::tmem_ld_32x32(t_row + c * kStN, r);
+        if (DUAL) tc::tmem_ld_32x32(t_row + (2 + c) * kStN, reinterpret_cast<uint32_t(&)[32]>(r2));
+        tc::tmem_ld_wait();
+        const int p = row + c * BM;
+        if (p < kStPx) {
+          float* u = smem_u + p * 27;
+#pragma unroll
+          for (int n = 0; n < 27; ++n)
+            u[n] = DUAL ? fmaf(sc, __uint_as_float(r2[n]), __uint_as_float(r[n])) : __uint_as_float(r[n]);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+      tc::named_bar_sync(1, 128);                      // the 180 x 27 table of this tile is complete
+      const int h = th * kWsTH + out_r, w = tw * kWsTW + out_c;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float* u = smem_u + ((out_r + t / 3) * kPatchW + out_c + t % 3) * 27 + t * 3;
+        o0 += u[0]; o1 += u[1]; o2 += u[2];
+      }
+      if (h < g.H && w < g.W && !(g.dbg & 1)) {
+        const long long q = (long long)h * g.W + w;
+        gx[q] = o0; gx[plane + q] = o1; gx[2 * plane + q] = o2;
+      }
+      tc::named_bar_sync(1, 128);                      // everybody has read the table: the next tile may overwrite it
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
 // ================================================================================================
 // Weight-stationary halo reuse AND CTA pair, for the 128-channel layers at half resolution (conv2_1 forward,
 // conv2_2 both directions): N = 128 split over the two CTAs of a pair (64 weight rows each, all 9 taps x KB
@@ -1369,6 +1551,7 @@ struct TcConvPlan {
   CUtensorMap tmap_a, tmap_b;
   CUtensorMap tmap_a2;          // dual-source plans only (tc_conv_dual_plan_create)
   bool dual = false;
+  bool stencil = false;         // conv1_1 data gradient in 1x1 + stencil form (tc_conv_stencil_plan_create)
   CUtensorMap tmap_f, tmap_d;   // style fusion (tc_conv_set_style_fuse): activations of the blob below, scaled Gram difference
   bool sfuse = false;
   ConvGeom g;
@@ -1625,6 +1808,54 @@ static int launch_wsp(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __ha
   return 0;
 }
 
+// ---- conv1_1 data gradient, stencil form (tc_conv_first_stencil_kernel) -----------------------------------------
+int tc_conv_stencil_plan_create(st2_ctx* ctx, const __half* grad, const __half* act, const __half* w_all, int H, int W,
+                                TcConvPlan** out, int halo) {
+  if (W < 16 || H < 16) return st2_fail(ctx, ST2_ERR_ARG, "tc_conv: canvas too small for the conv1_1 gradient kernel");
+  TcConvPlan* p = new TcConvPlan();
+  ConvGeom& g = p->g;
+  memset(&g, 0, sizeof(g));
+  g.H = H; g.W = W; g.cin = 64; g.cout = 16; g.taps = 9;
+  g.hoff = halo;
+  g.TW = kWsTW; g.TH = kWsTH;
+  g.tiles_h = (H + g.TH - 1) / g.TH;
+  g.tiles_w = (W + g.TW - 1) / g.TW;
+  p->bn = 16; p->ws_kb = 1; p->pair = false; p->dual = (act != nullptr); p->stencil = true;
+  g.n_blocks = 1;
+  g.total_tiles = g.tiles_h * g.tiles_w;
+  g.cblocks = 1;
+  g.k_iters = 9;
+  cuuint64_t dims[3] = {64, (cuuint64_t)W, (cuuint64_t)(H + 2 * halo)};
+  cuuint64_t strides[2] = {128, (cuuint64_t)W * 128};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)kPatchW, (cuuint32_t)kPatchH};
+  int rc = st2_encode_tmap(ctx, &p->tmap_a, grad, 3, dims, strides, box);
+  if (!rc && act) rc = st2_encode_tmap(ctx, &p->tmap_a2, act, 3, dims, strides, box);
+  if (!rc) {
+    cuuint64_t wd[2] = {64, (cuuint64_t)(act ? 2 : 1) * kStN};
+    cuuint64_t ws[1] = {128};
+    cuuint32_t wb[2] = {(cuuint32_t)BK, (cuuint32_t)kStN};
+    rc = st2_encode_tmap(ctx, &p->tmap_b, w_all, 2, wd, ws, wb);
+  }
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return 0;
+}
+
+template <bool DUAL>
+static int launch_stencil(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* coef) {
+  const int n_pt = p->g.tiles_h * p->g.tiles_w;
+  const int grid = n_pt < ctx->sm_count ? n_pt : ctx->sm_count;
+  p->g.dbg = ctx->debug_flags;
+  if (p->g.rot)
+    tc_conv_first_stencil_kernel<DUAL, true><<<grid, kNumThreads, StCfg<DUAL>::kSmemBytes, ctx->stream>>>(
+        p->tmap_a, DUAL ? p->tmap_a2 : p->tmap_a, p->tmap_b, p->g, gx, coef);
+  else
+    tc_conv_first_stencil_kernel<DUAL, false><<<grid, kNumThreads, StCfg<DUAL>::kSmemBytes, ctx->stream>>>(
+        p->tmap_a, DUAL ? p->tmap_a2 : p->tmap_a, p->tmap_b, p->g, gx, coef);
+  ST2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 static void set_halo(TcConvPlan* p, const HaloArgs* halo) {
   if (halo != nullptr && halo->push_blocks > 0) { p->g.halo = *halo; p->g.rot = 1; }
   else { memset(&p->g.halo, 0, sizeof(p->g.halo)); p->g.rot = 0; }
@@ -1657,6 +1888,7 @@ int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const doubl
   if (!p || p->bn != 16 || (p->dual != (dual_coef != nullptr)))
     return st2_fail(ctx, ST2_ERR_ARG, "tc_conv_first_bwd: wrong plan");
   set_halo(p, halo);
+  if (p->stencil) return p->dual ? launch_stencil<true>(ctx, p, gx, dual_coef) : launch_stencil<false>(ctx, p, gx, nullptr);
   TcInject inj;
   inj.fc = nullptr; inj.sraw = nullptr; inj.coef = dual_coef; inj.pool = nullptr; inj.pool_wp = 0; inj.sfuse = 0;
   if (p->dual) return launch_ws<16, 2>(ctx, p, nullptr, nullptr, reinterpret_cast<__half*>(gx), EPI_RAW, inj);
@@ -1742,6 +1974,10 @@ int tc_conv_launch(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __half*
 
 #define ST2_BOTH(K, ...) {ST2_KFN(K<__VA_ARGS__, false>), SM}, {ST2_KFN(K<__VA_ARGS__, true>), SM}
 static St2SmemReg g_smem_conv_tc({
+    {ST2_KFN(tc_conv_first_stencil_kernel<false, false>), StCfg<false>::kSmemBytes},
+    {ST2_KFN(tc_conv_first_stencil_kernel<false, true>), StCfg<false>::kSmemBytes},
+    {ST2_KFN(tc_conv_first_stencil_kernel<true, false>), StCfg<true>::kSmemBytes},
+    {ST2_KFN(tc_conv_first_stencil_kernel<true, true>), StCfg<true>::kSmemBytes},
 #define SM Cfg<256>::kSmemBytes
     ST2_BOTH(tc_conv_kernel, 256),
 #undef SM
@@ -1772,7 +2008,10 @@ static St2SmemReg g_smem_conv_tc({
     {ST2_KFN(tc_conv_wsp_kernel<1>), WspCfg<1>::kSmemBytes}, {ST2_KFN(tc_conv_wsp_kernel<2>), WspCfg<2>::kSmemBytes}});
 #undef ST2_BOTH
 #define ST2_BOTH(K, ...) ST2_KFN(K<__VA_ARGS__, false>), ST2_KFN(K<__VA_ARGS__, true>)
-static St2KernelReg g_reg_conv_tc({ST2_BOTH(tc_conv_kernel, 256), ST2_BOTH(tc_conv_kernel, 128), ST2_BOTH(tc_conv_kernel, 64),
+static St2KernelReg g_reg_conv_tc({ST2_KFN(tc_conv_first_stencil_kernel<false, false>),
+                                      ST2_KFN(tc_conv_first_stencil_kernel<false, true>),
+                                      ST2_KFN(tc_conv_first_stencil_kernel<true, false>),
+                                      ST2_KFN(tc_conv_first_stencil_kernel<true, true>), ST2_BOTH(tc_conv_kernel, 256), ST2_BOTH(tc_conv_kernel, 128), ST2_BOTH(tc_conv_kernel, 64),
                                       ST2_BOTH(tc_conv_ws_kernel, 64, 1), ST2_BOTH(tc_conv_ws_kernel, 128, 1),
                                       ST2_BOTH(tc_conv_ws_kernel, 64, 2), ST2_BOTH(tc_conv_ws_kernel, 16, 1),
                                       ST2_BOTH(tc_conv_ws_kernel, 16, 2),

@@ -121,6 +121,12 @@ int tc_conv_first_bwd_launch(st2_ctx* ctx, TcConvPlan* p, float* gx, const doubl
 // `grad`, 64..127 for `act`); separate accumulators, combined in the epilogue with a device scalar.
 int tc_conv_dual_plan_create(st2_ctx* ctx, const __half* grad, const __half* act, const __half* w_dual, int H, int W,
                              TcConvPlan** out, int halo = 0);
+// The same convolution in "1x1 + stencil" form (one pointwise 64 -> 27 contraction of every patch pixel, then each
+// output pixel sums its 9 x 3 neighbours in shared memory): 8 MMAs per tile and source instead of 36.  act = nullptr:
+// gradient source only.  w_all: [sources][32 rows = tap' * 3 + plane (27 used)][64 ch] fp16.  Launched through
+// tc_conv_first_bwd_launch like the other two plans.
+int tc_conv_stencil_plan_create(st2_ctx* ctx, const __half* grad, const __half* act, const __half* w_all, int H, int W,
+                                TcConvPlan** out, int halo = 0);
 // ---- st2_conv_first_tc.cu: conv1_1 forward on the tensor cores (sliding-window K over pixel pairs) ---------
 struct TcFirstPlan;
 int tc_first_plan_create(st2_ctx* ctx, int H, int W, int halo_strip, TcFirstPlan** out);

@@ -131,8 +131,8 @@ __global__ void style_scale_kernel(const float* __restrict__ D, __half* __restri
 // written once at plan creation), 64..127 = W' (activation channels, rewritten here every evaluation).
 __global__ void __launch_bounds__(128)
 style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ gsum_local,
-                  const float* __restrict__ w_oihw, __half* __restrict__ wdual, double n_total, double* sb,
-                  double* raw_sum) {
+                  const float* __restrict__ w_oihw, __half* __restrict__ wdual, int stencil_layout, double n_total,
+                  double* sb, double* raw_sum) {
   // gsum_local (row strips): THIS strip's un-normalised Gram sum F^T F, so that the strip contributes exactly its own
   // sum_p |D' F_p|^2 to the all-reduced total (like a strip that does not fold); nullptr: the whole canvas,
   // F^T F = (D + A) C HW.
@@ -148,7 +148,9 @@ style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, cons
     float acc = 0.f;
 #pragma unroll 8
     for (int i = 0; i < C; ++i) acc = fmaf(__ldg(w_oihw + ((i * 3 + plane) * 3 + r) * 3 + sx), __ldg(D + i * C + j), acc);
-    wdual[(plane * 9 + tapf) * 128 + 64 + j] = __float2half_rn(acc * ds);
+    // stencil_layout: [source 1][row = tap' * 3 + plane][64]; else the dual pack [plane][tap'][128], channels 64..127
+    if (stencil_layout) wdual[(32 + tapf * 3 + plane) * C + j] = __float2half_rn(acc * ds);
+    else wdual[(plane * 9 + tapf) * 128 + 64 + j] = __float2half_rn(acc * ds);
   }
   double tot = 0.0;
   if (idx < C * C) {
@@ -190,6 +192,13 @@ __global__ void dual_pack_kernel(const __half* __restrict__ wbwd, __half* __rest
   if (idx >= 16 * 9 * 64) return;
   const int j = idx % 64, rt = idx / 64;
   wdual[rt * 128 + j] = wbwd[idx];
+}
+// ... -> the stencil form's pointwise weights [row = tap' * 3 + plane (27 of 32)][64] (tc_conv_first_stencil_kernel)
+__global__ void stencil_pack_kernel(const __half* __restrict__ wbwd, __half* __restrict__ wall) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 27 * 64) return;
+  const int j = idx % 64, row = idx / 64, tapf = row / 3, plane = row % 3;
+  wall[idx] = wbwd[(plane * 9 + tapf) * 64 + j];
 }
 
 // worker.py:249-277: freeze normalisers on first use, derive combine coefficients and trace values
@@ -896,18 +905,23 @@ static int eval_mid_impl(st2_plan* pl) {
     }
     ProfScope ps(ctx, 4);
     if (b == 1 && fold_eligible(pl, b)) {
+      const bool stencil = !ctx->knobs.no_stencil;
       if (!B.wfold) {
         if ((rc = ensure(ctx, (void**)&B.wfold, sizeof(__half) * 16 * 9 * 128))) return rc;
         ST2_CUDA(ctx, cudaMemsetAsync(B.wfold, 0, sizeof(__half) * 16 * 9 * 128, ctx->stream));
-        dual_pack_kernel<<<cdiv(16 * 9 * 64, 256), 256, 0, ctx->stream>>>(ctx->wh_bwd[0], B.wfold);
+        if (stencil) stencil_pack_kernel<<<cdiv(27 * 64, 256), 256, 0, ctx->stream>>>(ctx->wh_bwd[0], B.wfold);
+        else dual_pack_kernel<<<cdiv(16 * 9 * 64, 256), 256, 0, ctx->stream>>>(ctx->wh_bwd[0], B.wfold);
         ST2_LAUNCH_CHECK(ctx);
       }
-      if (!B.tc_sfold && (rc = tc_conv_dual_plan_create(ctx, (const __half*)(pl->strip ? B.grad_pad : B.grad),
-                                                        (const __half*)(pl->strip ? B.act_pad : B.act), B.wfold, B.H, B.W,
-                                                        &B.tc_sfold, pl->strip ? 1 : 0)))
-        return rc;
+      if (!B.tc_sfold) {
+        const __half* gsrc = (const __half*)(pl->strip ? B.grad_pad : B.grad);
+        const __half* asrc = (const __half*)(pl->strip ? B.act_pad : B.act);
+        rc = stencil ? tc_conv_stencil_plan_create(ctx, gsrc, asrc, B.wfold, B.H, B.W, &B.tc_sfold, pl->strip ? 1 : 0)
+                     : tc_conv_dual_plan_create(ctx, gsrc, asrc, B.wfold, B.H, B.W, &B.tc_sfold, pl->strip ? 1 : 0);
+        if (rc) return rc;
+      }
       style_fold_kernel<<<32, 128, 0, ctx->stream>>>(B.D, B.gram_target, pl->strip ? pl->gram_local[1] : nullptr,
-                                                     ctx->w_oihw[0], B.wfold, B.n_total(), sb, raw_sum);
+                                                     ctx->w_oihw[0], B.wfold, stencil ? 1 : 0, B.n_total(), sb, raw_sum);
       ST2_LAUNCH_CHECK(ctx);
       pl->inj[b].sraw = nullptr;
       pl->inj[b].fold = true;
@@ -1052,6 +1066,7 @@ int st2_ctx_create(int device, st2_ctx** out) {
     k.no_style_fuse = getenv("ST2_NO_STYLE_FUSE") != nullptr;
     k.no_graph = getenv("ST2_NO_GRAPH") != nullptr;
     k.no_inkernel_halo = getenv("ST2_NO_INKERNEL_HALO") != nullptr;
+    k.no_stencil = getenv("ST2_NO_STENCIL") != nullptr;
     if (const char* v = getenv("ST2_TC_BN")) k.tc_bn = atoi(v);
     if (const char* v = getenv("ST2_PAIR_MIN_TILES")) k.pair_min_tiles = atoll(v);
   }
@@ -1070,6 +1085,7 @@ void st2_ctx_destroy(st2_ctx* ctx) {
     cudaFree(ctx->wh_fwd[i]); cudaFree(ctx->wh_bwd[i]);
   }
   cudaFree(ctx->wh_first);
+  cudaFree(ctx->wh_bwd_all);
   cudaFree(ctx->dot_scratch);
   delete ctx;
 }
@@ -1148,6 +1164,12 @@ int st2_set_conv_weights(st2_ctx* ctx, int ci, const float* w, const float* b, i
                                                                        ctx->wf32_bwd[ci], ctx->wh_fwd[ci], ctx->wh_bwd[ci]);
   ST2_LAUNCH_CHECK(ctx);
   if (ci == 0 && (rc = tc_first_pack_weights(ctx, ctx->w_oihw[0], ctx->wh_first))) return rc;
+  if (ci == 0) {
+    if ((rc = ensure(ctx, (void**)&ctx->wh_bwd_all, sizeof(__half) * 32 * 64))) return rc;
+    ST2_CUDA(ctx, cudaMemsetAsync(ctx->wh_bwd_all, 0, sizeof(__half) * 32 * 64, ctx->stream));
+    stencil_pack_kernel<<<cdiv(27 * 64, 256), 256, 0, ctx->stream>>>(ctx->wh_bwd[0], ctx->wh_bwd_all);
+    ST2_LAUNCH_CHECK(ctx);
+  }
   ST2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // host buffers may be freed by the caller
   return 0;
 }
@@ -1199,8 +1221,11 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
     const int halo = strip ? 1 : 0;
     if (ctx->wh_bwd[0] && pl->b[1].H >= 16 && pl->b[1].W >= 16 && !ctx->knobs.no_tc_first) {
       Blob& c11 = pl->b[1];
-      int rc = tc_conv_plan_create(ctx, (const __half*)(strip ? c11.grad_pad : c11.grad), ctx->wh_bwd[0], c11.H, c11.W, 64, 16,
-                                   9, &c11.tc_bwd, halo);
+      int rc = ctx->wh_bwd_all && !ctx->knobs.no_stencil
+                   ? tc_conv_stencil_plan_create(ctx, (const __half*)(strip ? c11.grad_pad : c11.grad), nullptr,
+                                                 ctx->wh_bwd_all, c11.H, c11.W, &c11.tc_bwd, halo)
+                   : tc_conv_plan_create(ctx, (const __half*)(strip ? c11.grad_pad : c11.grad), ctx->wh_bwd[0], c11.H,
+                                         c11.W, 64, 16, 9, &c11.tc_bwd, halo);
       if (rc) return rc;
       if (ctx->wh_first && (rc = tc_first_plan_create(ctx, c11.H, c11.W, halo, &c11.tc_first))) return rc;
     }
@@ -1536,5 +1561,5 @@ int st2_gram_nchw(st2_ctx* ctx, const float* x, int C, long long HW, float* out)
 }  // extern "C"
 
 static St2KernelReg g_reg_net({ST2_KFN(halo_exchange_kernel), ST2_KFN(pack_x_kernel),
-                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(style_fold_kernel), ST2_KFN(style_rawsq_kernel), ST2_KFN(dual_pack_kernel), ST2_KFN(scatter_sums_kernel),
+                                  ST2_KFN(clear_volatile_kernel), ST2_KFN(style_scale_kernel), ST2_KFN(style_fold_kernel), ST2_KFN(style_rawsq_kernel), ST2_KFN(dual_pack_kernel), ST2_KFN(stencil_pack_kernel), ST2_KFN(scatter_sums_kernel),
                                   ST2_KFN(coef_kernel), ST2_KFN(final_kernel), ST2_KFN(pack_weights_kernel)});
