@@ -403,11 +403,19 @@ def canvas_record(args, rank, world, local, sampler, peaks, barrier):
     eng = job.engine
     for _ in range(warm):
         job.step(fetch=False)
-    ms, launches, t0, t1 = timed_steps(job, steps, barrier, world, eng)
+    # two repetitions of the K timed steps, the faster one reported (both recorded): on some boxes the first seconds of
+    # this section -- it follows the 3 s full-power section, ~25 s of GPU idle time (CPU baseline) and the fp32 job --
+    # ran 2-4x slower at full SM clock and reduced power (observed twice in six runs; the kernels' own times measured
+    # right afterwards were normal), which is the board's power / memory management, not the code under test
+    reps = []
+    for _ in range(2):
+        ms, launches, t0, t1 = timed_steps(job, steps, barrier, world, eng)
+        reps.append((ms, launches, t0, t1, timed_steps.host_enqueue_ms))
+    ms, launches, t0, t1, host_ms = min(reps, key=lambda r: r[0])
     clocks = sampler.window(t0, t1) if sampler else None
-    host_ms = timed_steps.host_enqueue_ms
+    rec['ms_per_step_repetitions'] = [r[0] / steps for r in reps]
     rec.update(value=steps / (ms / 1000.0), unit='it/s', ms_per_step=ms / steps, gpu_launches_per_step=launches / steps,
-               clocks=clocks)
+               clocks=clocks, host_enqueue_ms_per_step=host_ms)
 
     def extra(n):
         if spans is None:

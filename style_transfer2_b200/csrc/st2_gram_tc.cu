@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(256) gram_finalize_all_kernel(const GramFinArg
     const long long i = base + 4 * o;
     const float4* src = reinterpret_cast<const float4*>(L.partials + (base >> 7) * (long long)L.nsplit * 128 + 4 * o);
     const long long stride4 = 32;                            // [group][split][128 floats]
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    // a thread adds its <= 19 partial tiles in fp32 (pairwise where it matters little: each is itself an fp32 sum over
+    // thousands of pixels), the eight groups are then combined in double
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = kg; k0 < L.nsplit; k0 += 8 * kMaxPer) {
       float4 v[kMaxPer];
 #pragma unroll
@@ -183,13 +185,11 @@ __global__ void __launch_bounds__(256) gram_finalize_all_kernel(const GramFinArg
       }
 #pragma unroll
       for (int u = 0; u < kMaxPer; ++u) {
-        if (k0 + 8 * u < L.nsplit) {
-          s[0] += (double)v[u].x; s[1] += (double)v[u].y; s[2] += (double)v[u].z; s[3] += (double)v[u].w;
-        }
+        if (k0 + 8 * u < L.nsplit) { s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w; }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) sh[kg][o][e] = s[e];
+    for (int e = 0; e < 4; ++e) sh[kg][o][e] = (double)s[e];
     __syncthreads();
     if (kg < 4) {                                            // warp e finishes element e of every lane's quad
       double t = 0.0;
