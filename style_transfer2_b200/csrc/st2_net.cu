@@ -1067,6 +1067,7 @@ int st2_ctx_create(int device, st2_ctx** out) {
     k.no_graph = getenv("ST2_NO_GRAPH") != nullptr;
     k.no_inkernel_halo = getenv("ST2_NO_INKERNEL_HALO") != nullptr;
     k.no_stencil = getenv("ST2_NO_STENCIL") != nullptr;
+    k.ws128 = getenv("ST2_WS128") != nullptr;
     if (const char* v = getenv("ST2_TC_BN")) k.tc_bn = atoi(v);
     if (const char* v = getenv("ST2_PAIR_MIN_TILES")) k.pair_min_tiles = atoll(v);
   }
@@ -1232,7 +1233,10 @@ static int plan_create_common(st2_ctx* ctx, int H, int W, int prec, bool strip, 
     for (int i = 2; i < ST2_NUM_BLOBS; ++i) {
       if (g_blobs[i].kind != KIND_CONV) continue;
       const int ci = g_blobs[i].conv_index;
-      if (!ctx->wh_fwd[ci]) return st2_fail(ctx, ST2_ERR_STATE, "load weights before creating an fp16 plan");
+      if (!ctx->wh_fwd[ci]) {
+        if (ci > 0 && ctx->wh_fwd[1] == nullptr) return st2_fail(ctx, ST2_ERR_STATE, "load weights before creating an fp16 plan");
+        continue;        // a network cut below this layer: no weights, never evaluated (st2_forward reports it)
+      }
       Blob& cur = pl->b[i];
       Blob& below = pl->b[i - 1];
       int rc = tc_conv_plan_create(ctx, (const __half*)(strip ? below.act_pad : below.act), ctx->wh_fwd[ci], cur.H, cur.W,

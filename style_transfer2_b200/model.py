@@ -48,6 +48,8 @@ class Engine:
 
     def load_weights(self, params):
         for idx, name in enumerate(vgg.CONVS):
+            if name not in params:               # a network cut below this layer (vgg.net_from_prototxt): never evaluated
+                continue
             w, b = params[name]
             w = np.ascontiguousarray(w, np.float32)
             b = np.ascontiguousarray(b, np.float32)
@@ -205,9 +207,15 @@ class B200Model:
 
     # -- worker.py:58-61
     def reload_net(self):
+        self._n_blobs = len(vgg.BLOBS)
         if self.prototxt and os.path.exists(self.prototxt):
+            # the blobs the prototxt describes: the reference's truncated VGG-19, a shorter cut of it, or a deploy
+            # file with the classifier tail still attached (ignored: the path never evaluates it)
             with open(self.prototxt) as f:
-                vgg.check_prototxt(f.read())
+                blobs, ignored = vgg.net_from_prototxt(f.read(), strict=False)
+            self._n_blobs = len(blobs)
+            if ignored:
+                logger.warning('Ignoring %d layer(s) above %s: %s', len(ignored), blobs[-1][0], ', '.join(ignored))
         params = self._params
         if params is None and self.caffemodel and os.path.exists(self.caffemodel):
             params = vgg.read_caffemodel(self.caffemodel)
@@ -233,7 +241,7 @@ class B200Model:
 
     # -- worker.py:73-75
     def layers(self):
-        return list(vgg.BLOBS)
+        return list(vgg.BLOBS[:getattr(self, '_n_blobs', len(vgg.BLOBS))])
 
     def plan(self, height, width, keep=3):
         """Plan for a canvas size (reshape-on-demand, worker.py:84); a few sizes stay cached."""
@@ -280,6 +288,8 @@ class B200Model:
         plan = self.plan(image.shape[2], image.shape[3])
         x = torch.from_numpy(image).to(self.engine.device)
         top = max((vgg.BLOB_INDEX[n] for n in names), default=0)
+        if top >= self._n_blobs:
+            raise KeyError('%s is not a blob of this network (%s is its last)' % (vgg.BLOBS[top], self.layers()[-1]))
         plan.forward(x, top)
         self._last_plan, self._last_x = plan, x
         out = OrderedDict()

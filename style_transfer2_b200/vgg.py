@@ -47,7 +47,7 @@ def parse_prototxt_layers(text):
     with name, type, bottom, top and (conv) num_output/pad/kernel_size, (pool) pool/kernel_size/stride."""
     layers = []
     for body in _layer_bodies(text):
-        d = {}
+        d = {'_body': body}
         for key in ('name', 'type', 'bottom', 'top'):
             m = re.search(r'\b%s\s*:\s*"([^"]*)"' % key, body)
             if m:
@@ -77,12 +77,46 @@ def _layer_bodies(text):
         i = j
 
 
-def check_prototxt(text):
-    """Raise ValueError unless the prototxt describes exactly the truncated VGG-19 this engine
-    implements (same blob names and order, 3x3 pad-1 convs, 2x2/2 MAX pools, in-place ReLUs)."""
-    blobs = []
+_V1_TYPES = {'CONVOLUTION': 'Convolution', 'RELU': 'ReLU', 'POOLING': 'Pooling', 'INNER_PRODUCT': 'InnerProduct',
+             'DROPOUT': 'Dropout', 'SOFTMAX': 'Softmax', 'DATA': 'Data'}
+
+
+def _top_level_inputs(text):
+    """``input: "data"`` declarations outside any layer block (deploy-style prototxts, both dialects)."""
+    depth, out, i = 0, [], 0
+    for m in re.finditer(r'[{}]|\binput\s*:\s*"([^"]*)"', text):
+        tok = m.group(0)
+        if tok == '{':
+            depth += 1
+        elif tok == '}':
+            depth -= 1
+        elif depth == 0:
+            out.append(m.group(1))
+    return out
+
+
+def net_from_prototxt(text, strict=True):
+    """The blob list a prototxt describes, as far as this engine implements it.
+
+    Accepts the current dialect (``layer { type: "Convolution" }``, an ``Input`` layer) and the legacy V1 one
+    (``layers { type: CONVOLUTION }``, top-level ``input: "data"``), i.e. the reference's ``models/vgg19.prototxt``
+    (vgg19.prototxt:1-337) as well as the model zoo's VGG-19 deploy files.  The convolutional stack must be a PREFIX
+    of the VGG-19 topology above (3x3 pad-1 stride-1 convolutions with in-place ReLUs, 2x2/2 MAX pools, the same blob
+    names, order and widths) -- a network cut earlier (say after conv4_2) is fine and simply exposes fewer blobs.
+    ``strict=False`` additionally tolerates a tail the style-transfer path never evaluates (InnerProduct / Dropout /
+    Softmax after the last pool: the reference's file is the zoo's with exactly that tail removed) and returns its
+    layer names.  Returns ``(blobs, ignored)``; raises ValueError for anything else."""
+    blobs = [(name, 'input', 3) for name in _top_level_inputs(text)[:1]]
+    ignored = []
     for layer in parse_prototxt_layers(text):
         kind = layer.get('type')
+        if kind is None:
+            m = re.search(r'\btype\s*:\s*([A-Z_]+)', layer.get('_body', ''))
+            kind = m.group(1) if m else None
+        kind = _V1_TYPES.get(kind, kind)
+        if ignored:                                  # once the tail has begun nothing of it is interpreted
+            ignored.append(layer.get('name', '?'))
+            continue
         if kind == 'Input':
             blobs.append((layer['top'], 'input', 3))
         elif kind == 'Convolution':
@@ -94,10 +128,21 @@ def check_prototxt(text):
                 raise ValueError('unsupported pooling in %s' % layer.get('name'))
             blobs.append((layer['top'], 'pool', blobs[-1][2]))
         elif kind == 'ReLU':
-            if layer.get('bottom') != layer.get('top') or layer.get('top') != blobs[-1][0]:
+            if layer.get('bottom') != layer.get('top') or not blobs or layer.get('top') != blobs[-1][0]:
                 raise ValueError('ReLU %s is not in place on the preceding conv' % layer.get('name'))
+        elif not strict and kind in ('InnerProduct', 'Dropout', 'Softmax') and blobs and blobs[-1][1] == 'pool':
+            ignored.append(layer.get('name', '?'))
         else:
             raise ValueError('unsupported layer type %r' % kind)
+    if len(blobs) < 2 or blobs != TOPOLOGY[:len(blobs)]:
+        raise ValueError('prototxt does not describe (a prefix of) the truncated VGG-19 topology')
+    return blobs, ignored
+
+
+def check_prototxt(text):
+    """Raise ValueError unless the prototxt describes exactly the truncated VGG-19 of the reference
+    (same blob names and order, 3x3 pad-1 convs, 2x2/2 MAX pools, in-place ReLUs)."""
+    blobs, _ = net_from_prototxt(text, strict=True)
     if blobs != TOPOLOGY:
         raise ValueError('prototxt does not describe the truncated VGG-19 topology')
     return True

@@ -221,3 +221,64 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
+
+
+def _proto_current(blobs, tail=''):
+    """A prototxt in the current dialect for a prefix of the VGG-19 stack (same shape as the reference's file)."""
+    out = ['name: "cut"', 'layer { name: "data" type: "Input" top: "data" input_param { shape { dim: 1 dim: 3 dim: 8 dim: 8 } } }']
+    prev = 'data'
+    for name, kind, c in blobs[1:]:
+        if kind == 'conv':
+            out.append('layer { name: "%s" type: "Convolution" bottom: "%s" top: "%s" convolution_param { num_output: %d '
+                       'pad: 1 kernel_size: 3 } }' % (name, prev, name, c))
+            out.append('layer { name: "relu%s" type: "ReLU" bottom: "%s" top: "%s" }' % (name[4:], name, name))
+        else:
+            out.append('layer { name: "%s" type: "Pooling" bottom: "%s" top: "%s" pooling_param { pool: MAX kernel_size: 2 '
+                       'stride: 2 } }' % (name, prev, name))
+        prev = name
+    return '\n'.join(out) + tail
+
+
+def _proto_v1(blobs, tail=''):
+    """The same in the legacy V1 dialect of the model zoo's VGG deploy files."""
+    out = ['name: "VGG_ILSVRC_19_layers"', 'input: "data"', 'input_dim: 10', 'input_dim: 3', 'input_dim: 224', 'input_dim: 224']
+    prev = 'data'
+    for name, kind, c in blobs[1:]:
+        if kind == 'conv':
+            out.append('layers { bottom: "%s" top: "%s" name: "%s" type: CONVOLUTION convolution_param { num_output: %d '
+                       'pad: 1 kernel_size: 3 } }' % (prev, name, name, c))
+            out.append('layers { bottom: "%s" top: "%s" name: "relu%s" type: RELU }' % (name, name, name[4:]))
+        else:
+            out.append('layers { bottom: "%s" top: "%s" name: "%s" type: POOLING pooling_param { pool: MAX kernel_size: 2 '
+                       'stride: 2 } }' % (prev, name, name))
+        prev = name
+    return '\n'.join(out) + tail
+
+
+def test_prototxt_prefix_cuts_v1_dialect_and_classifier_tail():
+    """(f)1: the prototxt is PARSED into the blob list the engine exposes: the reference's file, a VGG-19 cut earlier,
+    the model zoo's V1 deploy dialect, and a classifier tail above pool5 that the style-transfer path never evaluates."""
+    from style_transfer2_b200 import vgg
+    full = vgg.TOPOLOGY
+    blobs, ignored = vgg.net_from_prototxt(_proto_current(full))
+    assert blobs == full and ignored == []
+    cut = full[:vgg.BLOB_INDEX['conv4_2'] + 1]
+    blobs, ignored = vgg.net_from_prototxt(_proto_current(cut))
+    assert [b[0] for b in blobs][-1] == 'conv4_2' and len(blobs) == 14
+    with pytest.raises(ValueError):
+        vgg.check_prototxt(_proto_current(cut))                          # not the reference's exact net
+    blobs, _ = vgg.net_from_prototxt(_proto_v1(full))
+    assert blobs == full
+    tail = ('\nlayers { bottom: "pool5" top: "fc6" name: "fc6" type: INNER_PRODUCT inner_product_param { num_output: 4096 } }'
+            '\nlayers { bottom: "fc6" top: "fc6" name: "relu6" type: RELU }'
+            '\nlayers { bottom: "fc6" top: "fc6" name: "drop6" type: DROPOUT }'
+            '\nlayers { bottom: "fc6" top: "prob" name: "prob" type: SOFTMAX }')
+    with pytest.raises(ValueError):
+        vgg.net_from_prototxt(_proto_v1(full, tail), strict=True)
+    blobs, ignored = vgg.net_from_prototxt(_proto_v1(full, tail), strict=False)
+    assert blobs == full and ignored == ['fc6', 'relu6', 'drop6', 'prob']
+    bad = _proto_current(full).replace('num_output: 256', 'num_output: 192', 1)
+    with pytest.raises(ValueError):
+        vgg.net_from_prototxt(bad)
+    with pytest.raises(ValueError):
+        vgg.net_from_prototxt(_proto_current(full).replace('kernel_size: 3', 'kernel_size: 5', 1))
