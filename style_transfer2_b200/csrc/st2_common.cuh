@@ -59,7 +59,7 @@ struct st2_ctx {
   // production kernels): read ONCE in st2_ctx_create, never on a launch path
   struct Knobs {
     bool no_fused_inject = false, no_tc_gram = false, no_tc_first = false, no_ws = false, force_pair = false,
-         wsp = false, no_pair = false, no_pool_fusion = false, no_style_fuse = false, no_graph = false, no_inkernel_halo = false, no_stencil = false, ws128 = false;
+         wsp = false, no_pair = false, no_pool_fusion = false, no_style_fuse = false, no_graph = false, no_inkernel_halo = false, no_stencil = false, no_ws128 = false;
     int tc_bn = 0;
     long long pair_min_tiles = -1;
   } knobs;

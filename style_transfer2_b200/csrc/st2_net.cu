@@ -1067,7 +1067,7 @@ int st2_ctx_create(int device, st2_ctx** out) {
     k.no_graph = getenv("ST2_NO_GRAPH") != nullptr;
     k.no_inkernel_halo = getenv("ST2_NO_INKERNEL_HALO") != nullptr;
     k.no_stencil = getenv("ST2_NO_STENCIL") != nullptr;
-    k.ws128 = getenv("ST2_WS128") != nullptr;
+    k.no_ws128 = getenv("ST2_NO_WS128") != nullptr;
     if (const char* v = getenv("ST2_TC_BN")) k.tc_bn = atoi(v);
     if (const char* v = getenv("ST2_PAIR_MIN_TILES")) k.pair_min_tiles = atoll(v);
   }
