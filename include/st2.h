@@ -60,6 +60,7 @@ extern "C" {
 #define ST2_G_P_GRAD 12
 #define ST2_G_GRAD 13
 #define ST2_G_HALO_TIMEOUT 14     /* row strips: 1.0 when a halo wait timed out (a neighbour died) */
+#define ST2_G_PROTOCOL_ERROR 15   /* row strips: 1.0 when deferred sums were used before every normaliser was frozen */
 
 typedef struct st2_ctx st2_ctx;
 typedef struct st2_plan st2_plan;
@@ -172,6 +173,12 @@ int st2_strip_attach(st2_plan* plan, int side, const void* ipc_handle, st2_plan*
  * grad(conv1_1) then has another meaning, and strips read a row of each other's: enable only when EVERY strip of the
  * canvas holds >= 16 rows and >= 16 columns (the tensor-core conv1_1 kernels' minimum).  Off by default on strips. */
 int st2_strip_set_fold(st2_plan* plan, int enable);
+/* Steady state: once every active normaliser is frozen (any completed evaluation with the current weights), block 1
+ * is only needed for trace values, so its all-reduce can wait: with `enable`, st2_eval_end does not expect block 1 to
+ * be reduced yet, and the caller all-reduces blocks 1 and 2 (and whatever else it has, e.g. the L-BFGS dot products)
+ * in ONE collective between st2_eval_end and st2_eval_final: two all-reduces per iteration instead of four.  Using it
+ * before the normalisers are frozen sets ST2_G_PROTOCOL_ERROR. */
+int st2_strip_set_deferred(st2_plan* plan, int enable);
 /* which 0: Gram sums (fp32), 1: per-blob partial sums (f64), 2: six pixel-space sums (f64) */
 int st2_strip_reduce_block(st2_plan* plan, int which, void** dev_out, long long* count_out);
 /* 1 when a halo wait timed out since the plan was created -- SYNCHRONISES */

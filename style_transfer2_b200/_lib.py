@@ -24,7 +24,7 @@ RESAMPLE_LANCZOS, RESAMPLE_BILINEAR = 0, 1
  SB_D_GRAD, SB_S_DSCALE) = range(20)
 # global scalar fields (include/st2.h)
 (G_SCD_LOSS, G_TV_NORM, G_P_NORM, G_SCD_GRAD_SQ, G_T_GRAD_SQ, G_P_GRAD_SQ, G_GRAD_SQ, G_T_LOSS, G_P_LOSS,
- G_LOSS, G_SCD_GRAD, G_T_GRAD, G_P_GRAD, G_GRAD, G_HALO_TIMEOUT) = range(15)
+  G_LOSS, G_SCD_GRAD, G_T_GRAD, G_P_GRAD, G_GRAD, G_HALO_TIMEOUT, G_PROTOCOL_ERROR) = range(16)
 IPC_HANDLE_BYTES = 64
 
 _vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
@@ -68,6 +68,7 @@ _SIGS = {
     'st2_strip_ipc_handle': (_i, [_vp, _vp]),
     'st2_strip_attach': (_i, [_vp, _i, _vp, _vp, _i]),
     'st2_strip_set_fold': (_i, [_vp, _i]),
+    'st2_strip_set_deferred': (_i, [_vp, _i]),
     'st2_strip_reduce_block': (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(C.c_longlong)]),
     'st2_strip_halo_error': (_i, [_vp, _ip]),
     'st2_read_scalars': (_i, [_vp, _dp]),

@@ -202,39 +202,59 @@ __global__ void stencil_pack_kernel(const __half* __restrict__ wbwd, __half* __r
 }
 
 // worker.py:249-277: freeze normalisers on first use, derive combine coefficients and trace values
-__global__ void coef_kernel(EvalSpec es, double* scal) {
+// mode 0: everything.  Row strips with deferred sums (st2_strip_set_deferred): mode 1 before the backward pass -- the
+// combine coefficients only, from the FROZEN normalisers (the sums are not reduced yet; a normaliser that is not
+// frozen is a protocol error and raises the sticky flag); mode 2 after the merged all-reduce -- the trace values.
+__global__ void coef_kernel(EvalSpec es, double* scal, int mode) {
   const int k = threadIdx.x;
   if (k >= es.n) return;
   const int b = es.order[k];
   double* sb = scal + b * ST2_SCAL_PER_BLOB;
+  double* g = scal + ST2_SCAL_GLOBAL_BASE;
   const double n = es.nelem[b];
   const double C = (double)es.C[b];
+  const bool coefs = mode != 2, traces = mode != 1;
   if (w_on(es.cw[b])) {
     const double msd = sb[SB_C_SUMSQ] / n;
-    if (sb[SB_C_VALID] == 0.0) { sb[SB_C_NORM] = (2.0 / n) * sqrt(msd); sb[SB_C_VALID] = 1.0; }
+    if (sb[SB_C_VALID] == 0.0) {
+      if (mode == 0) { sb[SB_C_NORM] = (2.0 / n) * sqrt(msd); sb[SB_C_VALID] = 1.0; }
+      else g[ST2_G_PROTOCOL_ERROR] = 1.0;
+    }
     const double cn = sb[SB_C_NORM];
-    sb[SB_C_COEF] = (double)es.cw[b] / cn * (2.0 / n);
-    sb[SB_C_LOSS] = (double)es.cw[b] * msd / cn;
-    sb[SB_C_GRAD] = fabs((double)es.cw[b] / cn) * (2.0 / n) * sqrt(msd);
+    if (coefs) sb[SB_C_COEF] = (double)es.cw[b] / cn * (2.0 / n);
+    if (traces) {
+      sb[SB_C_LOSS] = (double)es.cw[b] * msd / cn;
+      sb[SB_C_GRAD] = fabs((double)es.cw[b] / cn) * (2.0 / n) * sqrt(msd);
+    }
   }
   if (w_on(es.sw[b])) {
     double ds = sb[SB_S_DSCALE];
     if (ds == 0.0) ds = 1.0;
     const double kk = 2.0 / (C * C * n);                       // 2 / (gram_diff.size * feat.size)
     const double raw2 = sb[SB_S_RAWSQ] / (ds * ds);
-    if (sb[SB_S_VALID] == 0.0) { sb[SB_S_NORM] = kk * sqrt(raw2 / n); sb[SB_S_VALID] = 1.0; }
+    if (sb[SB_S_VALID] == 0.0) {
+      if (mode == 0) { sb[SB_S_NORM] = kk * sqrt(raw2 / n); sb[SB_S_VALID] = 1.0; }
+      else g[ST2_G_PROTOCOL_ERROR] = 1.0;
+    }
     const double sn = sb[SB_S_NORM];
-    sb[SB_S_COEF] = (double)es.sw[b] / sn * kk / ds;
-    sb[SB_S_LOSS] = (double)es.sw[b] * (sb[SB_S_GRAMSQ] / (C * C)) / sn;
-    sb[SB_S_GRAD] = fabs((double)es.sw[b] / sn) * kk * sqrt(raw2 / n);
+    if (coefs) sb[SB_S_COEF] = (double)es.sw[b] / sn * kk / ds;
+    if (traces) {
+      sb[SB_S_LOSS] = (double)es.sw[b] * (sb[SB_S_GRAMSQ] / (C * C)) / sn;
+      sb[SB_S_GRAD] = fabs((double)es.sw[b] / sn) * kk * sqrt(raw2 / n);
+    }
   }
   if (w_on(es.dw[b])) {
     const double msf = sb[SB_D_SUMSQ] / n;
-    if (sb[SB_D_VALID] == 0.0) { sb[SB_D_NORM] = (2.0 / n) * sqrt(msf); sb[SB_D_VALID] = 1.0; }
+    if (sb[SB_D_VALID] == 0.0) {
+      if (mode == 0) { sb[SB_D_NORM] = (2.0 / n) * sqrt(msf); sb[SB_D_VALID] = 1.0; }
+      else g[ST2_G_PROTOCOL_ERROR] = 1.0;
+    }
     const double dn = sb[SB_D_NORM];
-    sb[SB_D_COEF] = (double)es.dw[b] / dn * (-2.0 / n);
-    sb[SB_D_LOSS] = -(double)es.dw[b] * msf / dn;
-    sb[SB_D_GRAD] = fabs((double)es.dw[b] / dn) * (2.0 / n) * sqrt(msf);
+    if (coefs) sb[SB_D_COEF] = (double)es.dw[b] / dn * (-2.0 / n);
+    if (traces) {
+      sb[SB_D_LOSS] = -(double)es.dw[b] * msf / dn;
+      sb[SB_D_GRAD] = fabs((double)es.dw[b] / dn) * (2.0 / n) * sqrt(msf);
+    }
   }
 }
 
@@ -433,6 +453,8 @@ struct st2_plan {
   bool strip = false, edge_top = true, edge_bot = true;
   bool async_halo = false;     // halo rows travel inside the consuming convolution kernels (all neighbours over IPC)
   bool strip_fold = false;     // every strip of the canvas folds conv1_1's style gradient (st2_strip_set_fold)
+  bool deferred_sums = false;  // st2_strip_set_deferred: block 1 is all-reduced after st2_eval_end, with block 2
+  bool eval_deferred = false;  // ... as decided for the evaluation in flight
   int rank = 0, world = 1, row0 = 0, H_total = 0;
   unsigned char* slab = nullptr;
   StripLayout lay;
@@ -977,13 +999,16 @@ static int eval_end_impl(st2_plan* pl, float* grad_out) {
   const EvalSpec& es = pl->es;
   const float* x = pl->eval_x;
   int rc = 0;
-  if (pl->strip) {
+  // deferred sums (steady state on strips): the per-blob sums are all-reduced AFTER the backward pass, together with
+  // the pixel sums (and the caller's L-BFGS dot products); the coefficients need only the frozen normalisers
+  pl->eval_deferred = pl->strip && pl->deferred_sums;
+  if (pl->strip && !pl->eval_deferred) {
     scatter_sums_kernel<<<1, 32, 0, ctx->stream>>>(pl->red, pl->scal);
     ST2_LAUNCH_CHECK(ctx);
   }
   if (es.n > 0) {
     ProfScope ps(ctx, 5);
-    coef_kernel<<<1, 32, 0, ctx->stream>>>(es, pl->scal);
+    coef_kernel<<<1, 32, 0, ctx->stream>>>(es, pl->scal, pl->eval_deferred ? 1 : 0);
     ST2_LAUNCH_CHECK(ctx);
   }
   double* gscal = pl->scal + ST2_SCAL_GLOBAL_BASE;
@@ -1016,6 +1041,14 @@ static int eval_end_impl(st2_plan* pl, float* grad_out) {
 static int eval_final_impl(st2_plan* pl) {
   st2_ctx* ctx = pl->ctx;
   if (pl->eval_phase != 3) return st2_fail(ctx, ST2_ERR_STATE, "st2_eval_final: call st2_eval_end first");
+  if (pl->eval_deferred) {
+    scatter_sums_kernel<<<1, 32, 0, ctx->stream>>>(pl->red, pl->scal);
+    ST2_LAUNCH_CHECK(ctx);
+    if (pl->es.n > 0) {
+      coef_kernel<<<1, 32, 0, ctx->stream>>>(pl->es, pl->scal, 2);
+      ST2_LAUNCH_CHECK(ctx);
+    }
+  }
   final_kernel<<<1, 32, 0, ctx->stream>>>(pl->es, pl->scal, pl->strip ? &reinterpret_cast<SlabHeader*>(pl->slab)->err : nullptr);
   ST2_LAUNCH_CHECK(ctx);
   pl->eval_phase = 0;
@@ -1308,6 +1341,12 @@ int st2_strip_set_fold(st2_plan* pl, int enable) {
   if (enable && pl->prec == ST2_PREC_FP16 && pl->b[1].tc_bwd == nullptr)
     return st2_fail(pl->ctx, ST2_ERR_STATE, "st2_strip_set_fold: this strip is too small for the tensor-core conv1_1 kernels");
   pl->strip_fold = enable != 0;
+  return 0;
+}
+
+int st2_strip_set_deferred(st2_plan* pl, int enable) {
+  if (!pl || !pl->strip) return st2_fail(pl ? pl->ctx : nullptr, ST2_ERR_ARG, "st2_strip_set_deferred: not a strip plan");
+  pl->deferred_sums = enable != 0;
   return 0;
 }
 

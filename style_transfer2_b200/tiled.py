@@ -96,6 +96,9 @@ class StripPlan(Plan):
     def eval_final(self):
         self._check(self.lib.st2_eval_final(self.handle), 'st2_eval_final')
 
+    def set_deferred(self, enable):
+        self._check(self.lib.st2_strip_set_deferred(self.handle, 1 if enable else 0), 'st2_strip_set_deferred')
+
     def set_fold(self, enable):
         self._check(self.lib.st2_strip_set_fold(self.handle, 1 if enable else 0), 'st2_strip_set_fold')
 
@@ -184,6 +187,10 @@ class TiledTransfer:
         self._norm_source = None
         self._dl = None
         self.loss = None
+        # every active normaliser is frozen (an evaluation with the current weights has completed): the per-blob sums
+        # are then needed for trace values only and their all-reduce merges with the later ones (st2_strip_set_deferred)
+        self._norms_frozen = False
+        self._deferred_on = None
         if height is not None:
             self._layout(int(height), int(width))
 
@@ -217,6 +224,8 @@ class TiledTransfer:
         self._content_done, self._style_done = set(), set()
         self._have_eval = False
         self._dl = None
+        self._norms_frozen = False
+        self._deferred_on = None
 
     def _release_strips(self):
         if self.strips:
@@ -427,6 +436,7 @@ class TiledTransfer:
         self.weights = pd.DataFrame.from_dict(weights, dtype=np.float32)
         self.params = params
         self._weights_dirty = True
+        self._norms_frozen = False               # a newly weighted layer freezes its normaliser at the next evaluation
         self.objective_changed()
 
     def objective_changed(self):
@@ -469,6 +479,7 @@ class TiledTransfer:
             st.plan.reset_norms()
         self._pending_norms = {}
         self._norm_source = None
+        self._norms_frozen = False
         self._new_optimizer_state()
         self._adam_items = self._adam_items2 = 0
         self.t = 0
@@ -596,9 +607,32 @@ class TiledTransfer:
             self._style_done.update(need_s)
 
     # ------------------------------------------------------------------ objective (worker.py:231-301)
-    def opfunc(self, return_grad=True):
-        """Collective evaluation at the strips' current x.  Returns (loss, [grad per local strip])."""
+    def _all_reduce_merged(self, blocks):
+        """One all-reduce for several small blocks: ``blocks`` = list of per-strip tensor lists (same dtype)."""
+        cats = []
+        for i, st in enumerate(self._each()):
+            cats.append(torch.cat([b[i] for b in blocks]))
+        self.all_reduce(cats)
+        for i, st in enumerate(self._each()):
+            off = 0
+            for b in blocks:
+                n = b[i].numel()
+                b[i].copy_(cats[i][off:off + n])
+                off += n
+
+    def opfunc(self, return_grad=True, extra_sums=None):
+        """Collective evaluation at the strips' current x.  Returns (loss, [grad per local strip]).
+
+        Four sum all-reduces in general (Gram sums; per-blob sums; pixel sums; the optimizer's own afterwards).  Once
+        every active normaliser is frozen the per-blob sums only feed trace values, so they travel with the pixel sums
+        after the backward pass -- and with ``extra_sums(grads)`` (the L-BFGS dot-product block, computed from the new
+        gradient): two all-reduces per iteration.  ``self.merged_extra`` tells the caller whether that happened."""
         self._sync_plans()
+        deferred = bool(return_grad and self._norms_frozen)
+        if deferred != self._deferred_on:
+            for st in self.strips:
+                st.plan.set_deferred(deferred)
+            self._deferred_on = deferred
         grads = []
         for st in self._each():
             if return_grad:
@@ -610,12 +644,22 @@ class TiledTransfer:
         self.all_reduce([st.plan.reduce_block(0) for st in self.strips])
         for st in self._each():
             st.plan.eval_mid()
-        self.all_reduce([st.plan.reduce_block(1) for st in self.strips])
+        if not deferred:
+            self.all_reduce([st.plan.reduce_block(1) for st in self.strips])
         for st, g in zip(self._each(), grads if return_grad else [None] * len(self.strips)):
             st.plan.eval_end(g)
-        self.all_reduce([st.plan.reduce_block(2) for st in self.strips])
+        self.merged_extra = False
+        if deferred:
+            blocks = [[st.plan.reduce_block(1) for st in self.strips], [st.plan.reduce_block(2) for st in self.strips]]
+            if extra_sums is not None:
+                blocks.append(extra_sums(grads))
+                self.merged_extra = True
+            self._all_reduce_merged(blocks)
+        else:
+            self.all_reduce([st.plan.reduce_block(2) for st in self.strips])
         for st in self._each():
             st.plan.eval_final()
+        self._norms_frozen = True
         st0 = self.strips[0]
         tr = LazyTrace(None, None, list(self._spec), return_grad, time.perf_counter())
         tr._host = host = self.engine.trace_slot(tr)
@@ -625,7 +669,8 @@ class TiledTransfer:
             tr._event = ev = torch.cuda.Event()
             ev.record(st0.stream)
         self.engine.sync_stream()
-        tr.halo_timeout = lambda tr=tr: bool(tr._host[_lib.SCAL_GLOBAL_BASE + _lib.G_HALO_TIMEOUT] != 0.0)
+        tr.halo_timeout = lambda tr=tr: bool(tr._host[_lib.SCAL_GLOBAL_BASE + _lib.G_HALO_TIMEOUT] != 0.0 or
+                                             tr._host[_lib.SCAL_GLOBAL_BASE + _lib.G_PROTOCOL_ERROR] != 0.0)
         self.traces.append(tr)
         self._norm_source = tr
         del self.traces[:-256]
@@ -653,10 +698,14 @@ class TiledTransfer:
             self.all_reduce(self._lbfgs_sums())
         for st in self._each():
             self._lcall(st, 'st2_lbfgs_advance_end', _ptr(st.x), _ptr(st.grad), float(self.step_size))
-        loss, grads = self.opfunc()
-        for st, g in zip(self._each(), grads):
-            self._lcall(st, 'st2_lbfgs_commit_begin', _ptr(g), _ptr(st.grad))
-        self.all_reduce(self._lbfgs_sums())
+        def commit_begin(grads):
+            for st, g in zip(self._each(), grads):
+                self._lcall(st, 'st2_lbfgs_commit_begin', _ptr(g), _ptr(st.grad))
+            return self._lbfgs_sums()
+
+        loss, grads = self.opfunc(extra_sums=commit_begin)     # steady state: the dot products ride with the loss sums
+        if not self.merged_extra:
+            self.all_reduce(commit_begin(grads))
         for st, g in zip(self._each(), grads):
             self._lcall(st, 'st2_lbfgs_commit_end')
             st.grad = g
@@ -686,7 +735,8 @@ class TiledTransfer:
 
     def _raise_on_halo_timeout(self, tr):
         if tr.halo_timeout():
-            raise RuntimeError('a halo exchange timed out: a neighbouring strip stopped (rank %d)' % self.strips[0].rank)
+            raise RuntimeError('a halo exchange timed out (a neighbouring strip stopped) or the deferred-sums protocol was '
+                               'used before the normalisers were frozen (rank %d)' % self.strips[0].rank)
 
     def step(self, fetch=True):
         """worker.py:303-310."""

@@ -176,6 +176,13 @@ def test_strips_follow_the_whole_canvas_trajectory(models, optimizer, steps, min
         assert tr['fevals'] == i + 1
         assert psnr(img, img_ref) > min_db, (i, psnr(img, img_ref))
         assert np.isclose(tr['loss'], tr_ref['loss'], rtol=1e-3)
+        # every trace value: from the second evaluation on the strips run the two-all-reduce protocol (per-blob sums
+        # deferred and merged with the pixel sums and the L-BFGS dot products, st2_strip_set_deferred)
+        assert list(tr) == list(tr_ref)
+        for k, v in tr_ref.items():
+            if k != 'time':
+                assert np.isclose(tr[k], v, rtol=2e-3), (i, k, tr[k], v)
+    assert tt._deferred_on is True
     tt.check()
     tt.close()
 
