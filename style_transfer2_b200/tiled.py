@@ -1,20 +1,23 @@
 """One large canvas split into row strips over several B200s (BASELINE config 4).
 
 The reference holds the whole image in one ``caffe.Net`` (worker.py:84-86) and caps its size
-(``max_size``, app.py:183-185); this module is the tiling scheduler that replaces that cap.  It
-mirrors the part of ``worker.StyleTransfer`` (worker.py:117-315) that a job needs --
-``set_input / set_content / set_style / set_weights / reset / opfunc / step`` -- for a canvas whose
-rows are partitioned over ``world`` strips:
+(``max_size``, app.py:183-185); this module is the tiling scheduler that replaces that cap.  ``TiledTransfer``
+is ``worker.StyleTransfer`` (worker.py:117-315) -- the whole state machine the worker drives:
+``set_input / resample_input / set_content / resample_content / set_style / set_weights /
+set_optimizer_class / reset / start / pause / check_consistency / opfunc / step / step_async`` -- for a
+canvas whose rows are partitioned over ``world`` strips (``Worker`` builds it when ``config.ini`` has
+``gpus`` / ``tiles``):
 
 * every strip owns rows ``[row0, row1)`` (boundaries at multiples of 32 rows, ``parallel.strip_bounds``)
   of x, of the gradient, of the L-BFGS history / Adam moments and of every activation;
 * before each 3x3 convolution (forward and data-gradient) the strips swap ONE boundary row.  libst2
-  does that itself: a push kernel stores the row into the neighbour's halo row through peer memory
-  (CUDA IPC mapping -> NVLink) and raises a flag there, the consumer spins on its flag in a 1-thread
-  kernel.  No NCCL, no host synchronisation on the halo path;
-* what remains are four small sum all-reduces per iteration, issued here between the phases of the
-  evaluation: the strips' Gram sums (<= 2.4 MB), 3 sums per weighted blob, 6 pixel-space sums, and the
-  L-BFGS dot-product block (one all-reduce per step thanks to the compact form, st2_lbfgs.cu).
+  does that itself through peer memory (CUDA IPC mapping -> NVLink): with one process per GPU the push
+  and the wait live INSIDE the convolution kernel that consumes the tensor; strips sharing a process
+  use a small exchange kernel.  No NCCL, no host synchronisation on the halo path;
+* what remains are small sum all-reduces, issued here between the phases of the evaluation: the
+  strips' Gram sums (<= 2.4 MB), 3 sums per weighted blob, 6 pixel-space sums, and the L-BFGS
+  dot-product block (one block per step thanks to the compact form, st2_lbfgs.cu) -- four collectives
+  in general, TWO per iteration once the normalisers are frozen (``opfunc``).
 
 Two ways to place the strips:
 * ``torch.distributed`` (one process per GPU, NCCL): each process holds the strip of its rank;
