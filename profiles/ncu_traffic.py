@@ -2,10 +2,8 @@
 """DRAM traffic of the tcgen05 conv launches of ONE iteration from an `ncu --set full` report.
 usage: python profiles/ncu_traffic.py gpurun_out/prof.ncu-rep [offset] > profiles/<round>_tcconv_traffic.json
 
-The capture must hold (at least) the 30 tensor-core convolution launches of one L-BFGS iteration, which come
-in a fixed cyclic order: 12 forward 3x3 convolutions (conv1_2 .. conv5_1), 5 style-gradient 1x1 contractions,
-12 data-gradient convolutions (conv5_1 .. conv1_2), the conv1_1 data gradient.  `offset` = position in that
-cycle of the first captured launch (0 when the capture starts on an iteration boundary).
+The capture must hold (at least) the tensor-core convolution launches of one whole L-BFGS iteration, which come in a
+fixed cyclic order (see CYCLE below); it may start anywhere.
 bench.py reads the JSON to fill roofline.traffic (bytes per 3x3 launch, averaged over the 24 of conv1_2..conv5_1)."""
 import csv
 import json
@@ -39,28 +37,30 @@ for r in rows[2:]:
                      'dram_read': to_bytes(r[ir], units[ir]), 'dram_write': to_bytes(r[iw], units[iw]),
                      'us_under_ncu': to_us(r[it], units[it]),
                      'tensor_pipe_pct': float(r[itp]) if itp is not None and r[itp] else None})
-# Round 2: conv1_1's style gradient is folded into its data-gradient weights, so an iteration has 29 tensor-core conv
-# launches: 12 forward 3x3 (conv1_2 .. conv5_1), 4 style-gradient 1x1 contractions (conv2_1 .. conv5_1), 12
-# data-gradient 3x3 (conv5_1 .. conv1_2) and the dual-source conv1_1 data gradient (tc_conv_ws_kernel<16, 2>), which
-# ends the cycle.  The capture may start anywhere: the cycle is located by that last kernel.
-CYCLE = 29
-ends = [i for i, l in enumerate(launches) if 'tc_conv_ws_kernel<16, 2' in l['kernel']]
+# Round 2 (final kernels): conv1_1's style gradient is folded into its data-gradient weights and conv2_1's is contracted
+# inside conv2_2's data-gradient kernel, so an iteration has 28 tensor-core conv launches: 12 forward 3x3
+# (conv1_2 .. conv5_1), 3 style-gradient 1x1 contractions (conv3_1, conv4_1, conv5_1), 12 data-gradient 3x3
+# (conv5_1 .. conv1_2) and the dual-source conv1_1 data gradient (tc_conv_first_stencil_kernel), which ends the cycle.
+# The capture may start anywhere: the cycle is located by that last kernel.
+CYCLE = 28
+END = 'tc_conv_first_stencil_kernel'
+ends = [i for i, l in enumerate(launches) if END in l['kernel']]
 start = next((e + 1 for e in ends if e + 1 + CYCLE <= len(launches)), None)
-assert start is not None, 'no complete iteration (29 launches after a tc_conv_ws_kernel<16, 2>) in the capture'
+assert start is not None, 'no complete iteration (28 launches after a %s) in the capture' % END
 launches = launches[start:start + CYCLE]
-assert 'tc_conv_ws_kernel<16, 2' in launches[-1]['kernel'], 'cycle misaligned'
+assert END in launches[-1]['kernel'], 'cycle misaligned'
 NAMES = ['conv1_2', 'conv2_1', 'conv2_2', 'conv3_1', 'conv3_2', 'conv3_3', 'conv3_4', 'conv4_1', 'conv4_2', 'conv4_3',
          'conv4_4', 'conv5_1']
 conv, style, first = [], [], []
 for pos, l in enumerate(launches):
     if pos < 12:
         l['what'] = NAMES[pos] + ' fwd'; conv.append(l)
-    elif pos < 16:
-        l['what'] = 'style grad %d (%s)' % (pos - 11, ['conv2_1', 'conv3_1', 'conv4_1', 'conv5_1'][pos - 12]); style.append(l)
-    elif pos < 28:
-        l['what'] = NAMES[27 - pos] + ' dgrad'; conv.append(l)
+    elif pos < 15:
+        l['what'] = 'style grad (%s)' % ['conv3_1', 'conv4_1', 'conv5_1'][pos - 12]; style.append(l)
+    elif pos < 27:
+        l['what'] = NAMES[26 - pos] + ' dgrad' + (' + conv2_1 style gradient' if NAMES[26 - pos] == 'conv2_2' else ''); conv.append(l)
     else:
-        l['what'] = 'conv1_1 dgrad + folded style gradient (dual source)'; first.append(l)
+        l['what'] = 'conv1_1 dgrad + folded style gradient (stencil form, dual source)'; first.append(l)
 assert len(conv) == 24
 tot = sum(l['dram_read'] + l['dram_write'] for l in conv)
 print(json.dumps({
