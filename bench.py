@@ -296,13 +296,19 @@ def profile_categories(eng, step, n, extra=None):
     """Per-category device time (CUDA events on the launch stream, st2_profile) over n steps."""
     import ctypes as C
     from style_transfer2_b200 import _lib
-    eng.call('st2_profile', 1)
+    eng.profile(True)
+    # a head start for the host: with two events around every launch span the host would otherwise trail the GPU, and
+    # a span whose kernel has not been enqueued yet when the GPU reaches its start event also counts the wait.  One
+    # 20 ms spin kernel in front of the n back-to-back steps (not one per step: the steps must run as densely as in the
+    # timed region) keeps the whole queue ahead of the device.
+    import torch
+    torch.cuda._sleep(int(0.020 * 1.9e9))
     for _ in range(n):
         step()
     ms_cat = (C.c_double * _lib.PROF_CATS)()
     n_cat = (C.c_longlong * _lib.PROF_CATS)()
     eng.call('st2_profile_read', ms_cat, n_cat)
-    eng.call('st2_profile', 0)
+    eng.profile(False)
     cats = {name: {'ms_per_step': ms_cat[i] / n, 'launch_spans_per_step': n_cat[i] / n}
             for i, name in enumerate(_lib.PROF_NAMES) if n_cat[i]}
     if extra:

@@ -77,7 +77,13 @@ class Engine:
         return self._ring[i]
 
     def launches(self):
-        return int(self.lib.st2_launch_count(self.ctx))
+        """Kernels launched through this context, incl. those replayed from CUDA graphs (worker._graph_step)."""
+        return int(self.lib.st2_launch_count(self.ctx)) + int(getattr(self, 'graph_launches', 0))
+
+    def profile(self, enable):
+        """Per-category CUDA-event timing (st2_profile); the graph path is bypassed while it is on."""
+        self.profiling = bool(enable)
+        self.call('st2_profile', 1 if enable else 0)
 
     def call(self, name, *args):
         _lib.check(self.ctx, getattr(self.lib, name)(self.ctx, *args), name)
