@@ -1,5 +1,6 @@
 // Shared declarations for libst2 (sm_100a only).  See include/st2.h for the C ABI.
 #pragma once
+#include <utility>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -59,7 +60,7 @@ struct st2_ctx {
   // production kernels): read ONCE in st2_ctx_create, never on a launch path
   struct Knobs {
     bool no_fused_inject = false, no_tc_gram = false, no_tc_first = false, no_ws = false, force_pair = false,
-         wsp = false, no_pair = false, no_pool_fusion = false, no_style_fuse = false, no_graph = false, no_inkernel_halo = false, no_stencil = false, no_ws128 = false;
+         wsp = false, no_pair = false, no_pool_fusion = false, no_style_fuse = false, no_graph = false, no_inkernel_halo = false, no_stencil = false, no_ws128 = false, no_pdl = false;
     int tc_bn = 0;
     long long pair_min_tiles = -1;
   } knobs;
@@ -114,6 +115,33 @@ struct St2SmemReg {
       return st2_fail((ctx), ST2_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
                       cudaGetErrorString(_e), __FILE__, __LINE__);                      \
   } while (0)
+
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// Every kernel of the steady-state iteration is launched with programmatic stream serialisation: it may be scheduled
+// while its predecessor in the stream is still draining, runs its prologue (barrier init, TMEM allocation, tensor-map
+// prefetch) in that shadow, and only pdl_wait() -- before its first access to global memory -- waits for the
+// predecessor to have completed and flushed.  pdl_trigger() at the top of a kernel lets ITS successor be scheduled as
+// soon as SM resources free up.  A kernel launched this way MUST execute pdl_wait() (all threads, before any global
+// load / store / atomic): the chain is transitive only because every link waits.  ST2_NO_PDL=1 launches plainly, for
+// which both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void st2_launch_pdl(st2_ctx* ctx, bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                           Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && !ctx->knobs.no_pdl) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);      // the error is picked up by ST2_LAUNCH_CHECK
+}
 
 // ---- device helpers --------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -38,6 +38,8 @@ struct FirstGeom { int H, W, tiles_h, tiles_w, hoff; };
 __global__ void pack_x8_kernel(const float* __restrict__ x, long long xps, uint4* __restrict__ x8, int H, int W, int lo,
                                int hi) {
   const long long total = (long long)(H + 2) * W;
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / W) - 1, w = (int)(i % W);
@@ -119,6 +121,7 @@ tc_conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pt = g.tiles_h * g.tiles_w;
+  pdl_trigger();
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_x); tc::prefetch_tmap(&tmap_o); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStagesF; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -130,6 +133,7 @@ tc_conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -283,11 +287,11 @@ int tc_first_fwd_launch(st2_ctx* ctx, TcFirstPlan* p, const float* x, long long 
   }
   long long blocks = ((long long)(H + 2) * W + 255) / 256;
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-  pack_x8_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(x, xps ? xps : (long long)H * W, p->x8, H, W, lo, hi);
+  st2_launch_pdl(ctx, true, pack_x8_kernel, (int)blocks, 256, 0, x, xps ? xps : (long long)H * W, p->x8, H, W, lo, hi);
   ST2_LAUNCH_CHECK(ctx);
   const int n_pt = p->g.tiles_h * p->g.tiles_w;
   const int grid = n_pt < ctx->sm_count ? n_pt : ctx->sm_count;
-  tc_conv_first_fwd_kernel<<<grid, kThreadsF, kSmemF, ctx->stream>>>(p->tmap_x, p->tmap_o, p->g, wpk, bias);
+  st2_launch_pdl(ctx, true, tc_conv_first_fwd_kernel, grid, kThreadsF, kSmemF, p->tmap_x, p->tmap_o, p->g, wpk, bias);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }

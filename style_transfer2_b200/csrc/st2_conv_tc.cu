@@ -317,6 +317,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (HALO) halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) {
@@ -332,6 +333,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();                      // everything above ran in the predecessor's shadow; global memory from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -560,6 +562,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  pdl_trigger();
   if (HALO) halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) {
@@ -575,6 +578,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   tc::fence_before_sync();
   tc::cluster_sync_all();
   tc::fence_after_sync();
+  pdl_wait();                      // everything above ran in the predecessor's shadow; global memory from here on
   const uint32_t tmem_base = *tmem_slot;
 
   // pair tiles: (n block fastest, then tile column, then pair-tile row), strided by the number of pairs
@@ -865,6 +869,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int nb = blockIdx.x % g.n_blocks;
   const int pt0 = blockIdx.x / g.n_blocks, pt_step = gridDim.x / g.n_blocks;
   const int n_pt = g.tiles_h * g.tiles_w;
+  pdl_trigger();
   if (HALO) halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) {
@@ -882,6 +887,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();                      // everything above ran in the predecessor's shadow; global memory from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -1201,6 +1207,7 @@ tc_conv_first_stencil_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pt = g.tiles_h * g.tiles_w;
+  pdl_trigger();
   if (HALO) halo_push_prologue(g.halo);
 
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmap_a); tc::prefetch_tmap(&tmap_b); if (DUAL) tc::prefetch_tmap(&tmap_a2); }
@@ -1214,6 +1221,7 @@ tc_conv_first_stencil_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();                      // everything above ran in the predecessor's shadow; global memory from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -1724,11 +1732,11 @@ static int launch_bn(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   p->g.step_tw = (grid / p->g.n_blocks) % p->g.tiles_w;
   p->g.step_th = (grid / p->g.n_blocks) / p->g.tiles_w;
   if (p->g.rot)
-    tc_conv_kernel<BN, true><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act,
-                                                                                      out, epi, out_scale, sumsq, inj);
+    st2_launch_pdl(ctx, false, tc_conv_kernel<BN, true>, grid, kNumThreads, Cfg<BN>::kSmemBytes, p->tmap_a, p->tmap_b, p->g,
+                   bias, act, out, epi, out_scale, sumsq, inj);
   else
-    tc_conv_kernel<BN, false><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, ctx->stream>>>(p->tmap_a, p->tmap_b, p->g, bias, act,
-                                                                                       out, epi, out_scale, sumsq, inj);
+    st2_launch_pdl(ctx, true, tc_conv_kernel<BN, false>, grid, kNumThreads, Cfg<BN>::kSmemBytes, p->tmap_a, p->tmap_b, p->g,
+                   bias, act, out, epi, out_scale, sumsq, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1760,11 +1768,11 @@ static int launch_ws(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __hal
   if (per_nb < 1) per_nb = 1;
   p->g.dbg = ctx->debug_flags;
   if (p->g.rot)
-    tc_conv_ws_kernel<BN, KB, true><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
-        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, tm, p->g, bias, act, out, epi, inj);
+    st2_launch_pdl(ctx, false, tc_conv_ws_kernel<BN, KB, true>, per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes,
+                   p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, tm, p->g, bias, act, out, epi, inj);
   else
-    tc_conv_ws_kernel<BN, KB, false><<<per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes, ctx->stream>>>(
-        p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, tm, p->g, bias, act, out, epi, inj);
+    st2_launch_pdl(ctx, true, tc_conv_ws_kernel<BN, KB, false>, per_nb * nbk, kNumThreads, WsCfg<BN, KB>::kSmemBytes,
+                   p->tmap_a, p->tmap_b, p->tmap_o, p->dual ? p->tmap_a2 : p->tmap_a, tm, p->g, bias, act, out, epi, inj);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1778,17 +1786,17 @@ static int launch_pair(st2_ctx* ctx, TcConvPlan* p, const float* bias, const __h
   p->g.dbg = ctx->debug_flags;
   if (SFUSE) {
     if (p->g.rot)
-      tc_conv2_kernel<128, true, true><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_f, p->tmap_d,
-                                                                                      p->g, bias, act, out, epi, inj);
+      st2_launch_pdl(ctx, false, tc_conv2_kernel<128, true, true>, 2 * pairs, kNumThreads, smem, p->tmap_a, p->tmap_b,
+                     p->tmap_f, p->tmap_d, p->g, bias, act, out, epi, inj);
     else
-      tc_conv2_kernel<128, false, true><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_f, p->tmap_d,
-                                                                                       p->g, bias, act, out, epi, inj);
+      st2_launch_pdl(ctx, true, tc_conv2_kernel<128, false, true>, 2 * pairs, kNumThreads, smem, p->tmap_a, p->tmap_b,
+                     p->tmap_f, p->tmap_d, p->g, bias, act, out, epi, inj);
   } else if (p->g.rot) {
-    tc_conv2_kernel<BN, true, false><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_a, p->tmap_b,
-                                                                                    p->g, bias, act, out, epi, inj);
+    st2_launch_pdl(ctx, false, tc_conv2_kernel<BN, true, false>, 2 * pairs, kNumThreads, smem, p->tmap_a, p->tmap_b,
+                   p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
   } else {
-    tc_conv2_kernel<BN, false, false><<<2 * pairs, kNumThreads, smem, ctx->stream>>>(p->tmap_a, p->tmap_b, p->tmap_a, p->tmap_b,
-                                                                                     p->g, bias, act, out, epi, inj);
+    st2_launch_pdl(ctx, true, tc_conv2_kernel<BN, false, false>, 2 * pairs, kNumThreads, smem, p->tmap_a, p->tmap_b,
+                   p->tmap_a, p->tmap_b, p->g, bias, act, out, epi, inj);
   }
   ST2_LAUNCH_CHECK(ctx);
   return 0;
@@ -1849,11 +1857,11 @@ static int launch_stencil(st2_ctx* ctx, TcConvPlan* p, float* gx, const double* 
   const int grid = n_pt < ctx->sm_count ? n_pt : ctx->sm_count;
   p->g.dbg = ctx->debug_flags;
   if (p->g.rot)
-    tc_conv_first_stencil_kernel<DUAL, true><<<grid, kNumThreads, StCfg<DUAL>::kSmemBytes, ctx->stream>>>(
-        p->tmap_a, DUAL ? p->tmap_a2 : p->tmap_a, p->tmap_b, p->g, gx, coef);
+    st2_launch_pdl(ctx, false, tc_conv_first_stencil_kernel<DUAL, true>, grid, kNumThreads, StCfg<DUAL>::kSmemBytes,
+                   p->tmap_a, DUAL ? p->tmap_a2 : p->tmap_a, p->tmap_b, p->g, gx, coef);
   else
-    tc_conv_first_stencil_kernel<DUAL, false><<<grid, kNumThreads, StCfg<DUAL>::kSmemBytes, ctx->stream>>>(
-        p->tmap_a, DUAL ? p->tmap_a2 : p->tmap_a, p->tmap_b, p->g, gx, coef);
+    st2_launch_pdl(ctx, true, tc_conv_first_stencil_kernel<DUAL, false>, grid, kNumThreads, StCfg<DUAL>::kSmemBytes,
+                   p->tmap_a, DUAL ? p->tmap_a2 : p->tmap_a, p->tmap_b, p->g, gx, coef);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }

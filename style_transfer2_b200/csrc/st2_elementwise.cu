@@ -44,6 +44,8 @@ inline int vgrid(long long items, int sm_count) {
 template <typename T>
 __global__ void pool_fwd_vec_kernel(const T* __restrict__ in, T* __restrict__ out, int C, int H, int W, int Ho,
                                     int Wo) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int N = Vec16<T>::N;
   const int cv = C / N;
   const long long total = (long long)Ho * Wo * cv;
@@ -80,6 +82,8 @@ __global__ void pool_fwd_vec_kernel(const T* __restrict__ in, T* __restrict__ ou
 template <typename T>
 __global__ void pool_bwd_vec_kernel(const T* __restrict__ act, const T* __restrict__ gp, T* __restrict__ gout,
                                     int C, int H, int W, int Ho, int Wo, int apply_mask) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int N = Vec16<T>::N;
   const int cv = C / N;
   const long long total = (long long)Ho * Wo * cv;
@@ -143,6 +147,8 @@ template <typename T>
 __global__ void combine_vec_kernel(const T* __restrict__ gin, const T* __restrict__ act, const T* __restrict__ fc,
                                    const T* __restrict__ sraw, T* __restrict__ out, long long nvec, int apply_mask,
                                    const double* __restrict__ coef, float h_cc, float h_sc, float h_dc) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int N = Vec16<T>::N;
   float cc = h_cc, sc = h_sc, dc = h_dc;
   if (coef != nullptr) { cc = (float)coef[0]; sc = (float)coef[1]; dc = (float)coef[2]; }
@@ -182,6 +188,8 @@ __global__ void combine_vec_kernel(const T* __restrict__ gin, const T* __restric
 template <typename T>
 __global__ void feature_sums_vec_kernel(const T* __restrict__ act, const T* __restrict__ fc, long long nvec,
                                         double* sum_diff_sq, double* sum_sq) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int N = Vec16<T>::N;
   float a = 0.f, b = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
@@ -209,8 +217,8 @@ template <typename T>
 int launch_pool_fwd_v(st2_ctx* ctx, const T* in, T* out, int C, int H, int W) {
   if (C % Vec16<T>::N) return launch_pool_fwd<T>(ctx, in, out, C, H, W);
   const int Ho = pool_extent(H), Wo = pool_extent(W);
-  pool_fwd_vec_kernel<T><<<vgrid((long long)Ho * Wo * (C / Vec16<T>::N), ctx->sm_count), kThreads, 0, ctx->stream>>>(
-      in, out, C, H, W, Ho, Wo);
+  st2_launch_pdl(ctx, true, pool_fwd_vec_kernel<T>, vgrid((long long)Ho * Wo * (C / Vec16<T>::N), ctx->sm_count), kThreads, 0,
+                 in, out, C, H, W, Ho, Wo);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -221,8 +229,8 @@ template <typename T>
 int launch_pool_bwd_v(st2_ctx* ctx, const T* act, const T* g_pool, T* g_out, int C, int H, int W, int apply_mask) {
   if (C % Vec16<T>::N) return launch_pool_bwd<T>(ctx, act, g_pool, g_out, C, H, W, apply_mask);
   const int Ho = pool_extent(H), Wo = pool_extent(W);
-  pool_bwd_vec_kernel<T><<<vgrid((long long)Ho * Wo * (C / Vec16<T>::N), ctx->sm_count), kThreads, 0, ctx->stream>>>(
-      act, g_pool, g_out, C, H, W, Ho, Wo, apply_mask);
+  st2_launch_pdl(ctx, true, pool_bwd_vec_kernel<T>, vgrid((long long)Ho * Wo * (C / Vec16<T>::N), ctx->sm_count), kThreads, 0,
+                 act, g_pool, g_out, C, H, W, Ho, Wo, apply_mask);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -234,9 +242,9 @@ int launch_combine_v(st2_ctx* ctx, const CombineArgs& a) {
   constexpr int N = Vec16<T>::N;
   if (a.n % N || !aligned16(a.gin) || !aligned16(a.act) || !aligned16(a.fc) || !aligned16(a.sraw) || !aligned16(a.out))
     return launch_combine<T>(ctx, a);
-  combine_vec_kernel<T><<<vgrid(a.n / N, ctx->sm_count), kThreads, 0, ctx->stream>>>(
-      (const T*)a.gin, (const T*)a.act, (const T*)a.fc, (const T*)a.sraw, (T*)a.out, a.n / N, a.apply_mask, a.coef,
-      a.h_cc, a.h_sc, a.h_dc);
+  st2_launch_pdl(ctx, true, combine_vec_kernel<T>, vgrid(a.n / N, ctx->sm_count), kThreads, 0, (const T*)a.gin,
+                 (const T*)a.act, (const T*)a.fc, (const T*)a.sraw, (T*)a.out, a.n / N, a.apply_mask, a.coef, a.h_cc,
+                 a.h_sc, a.h_dc);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -247,8 +255,8 @@ template <typename T>
 int launch_feature_sums_v(st2_ctx* ctx, const T* act, const T* fc, long long n, double* sum_diff_sq, double* sum_sq) {
   constexpr int N = Vec16<T>::N;
   if (n % N || !aligned16(act) || !aligned16(fc)) return launch_feature_sums<T>(ctx, act, fc, n, sum_diff_sq, sum_sq);
-  feature_sums_vec_kernel<T><<<vgrid(n / N / 4 + 1, ctx->sm_count), kThreads, 0, ctx->stream>>>(act, fc, n / N,
-                                                                                               sum_diff_sq, sum_sq);
+  st2_launch_pdl(ctx, true, feature_sums_vec_kernel<T>, vgrid(n / N / 4 + 1, ctx->sm_count), kThreads, 0, act, fc, n / N,
+                 sum_diff_sq, sum_sq);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }

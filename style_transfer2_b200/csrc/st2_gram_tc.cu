@@ -59,6 +59,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramGeom g, float
   const long long p_end = (p_begin + g.chunk < g.HW) ? p_begin + g.chunk : g.HW;
   const int k_iters = (int)((p_end - p_begin + KP - 1) / KP);
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) tc::prefetch_tmap(&tmap);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -69,6 +70,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramGeom g, float
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -164,6 +166,8 @@ __global__ void __launch_bounds__(256) gram_finalize_all_kernel(const GramFinArg
   // per iteration at 1024^2 and must keep that many bytes in flight, not chase one L2 round trip per split.
   const GramFinLayer L = a.l[blockIdx.y];
   __shared__ double sh[8][32][4];
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)L.C * L.C;                  // multiple of 4096
   const float denom = (float)((double)L.C * (double)L.HW);
   const int kg = threadIdx.x >> 5, o = threadIdx.x & 31;
@@ -262,7 +266,7 @@ void tc_gram_plan_destroy(TcGramPlan* p) {
 template <int GN>
 static int launch_gn(st2_ctx* ctx, TcGramPlan* p) {
   dim3 grid(p->g.m_tiles * p->g.n_tiles, p->g.splits);
-  tc_gram_kernel<GN><<<grid, kThreadsG, GCfg<GN>::kSmemBytes, ctx->stream>>>(p->tmap, p->g, p->partials);
+  st2_launch_pdl(ctx, true, tc_gram_kernel<GN>, grid, kThreadsG, GCfg<GN>::kSmemBytes, p->tmap, p->g, p->partials);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -287,7 +291,7 @@ int tc_gram_finalize_all(st2_ctx* ctx, int n, TcGramPlan* const* plans, const fl
     a.l[i].sum_dsq = sum_dsq ? sum_dsq[i] : nullptr;
     a.l[i].nsplit = plans[i]->g.splits; a.l[i].C = plans[i]->g.C; a.l[i].HW = plans[i]->g.HW;
   }
-  gram_finalize_all_kernel<<<dim3(ctx->sm_count * 2, n), 256, 0, ctx->stream>>>(a);
+  st2_launch_pdl(ctx, true, gram_finalize_all_kernel, dim3(ctx->sm_count * 2, n), 256, 0, a);
   ST2_LAUNCH_CHECK(ctx);
   return 0;
 }

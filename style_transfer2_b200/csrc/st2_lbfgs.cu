@@ -98,6 +98,8 @@ template <int V>
 __global__ void __launch_bounds__(kThreads, 1)
 lbfgs_pass_a(LbfgsDev* st_, const float* __restrict__ S, float* __restrict__ Y, const float* __restrict__ g_new,
              const float* __restrict__ g_prev, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const int count = st_->count, head = st_->head;
   const int pnew = (head + count) % SLOTS;
   const float* s = S + (long long)pnew * n;
@@ -144,6 +146,8 @@ template <int V>
 __global__ void __launch_bounds__(kThreads)
 lbfgs_pass_g(LbfgsDev* st_, const float* __restrict__ S, const float* __restrict__ Y, const float* __restrict__ g,
              long long n) {
+  pdl_trigger();
+  pdl_wait();
   const int count = st_->count, head = st_->head;
   float acc[2 * MAXM + 1];
 #pragma unroll
@@ -176,6 +180,8 @@ lbfgs_pass_g(LbfgsDev* st_, const float* __restrict__ S, const float* __restrict
 template <int V>
 __global__ void __launch_bounds__(kThreads)
 lbfgs_pass_y(LbfgsDev* st_, const float* __restrict__ S, const float* __restrict__ Y, long long n, int phys) {
+  pdl_trigger();
+  pdl_wait();
   const int count = st_->count, head = st_->head;
   const float* y = Y + (long long)phys * n;
   float acc[2 * MAXM];
@@ -213,6 +219,8 @@ __global__ void lbfgs_clear_sums(LbfgsDev* st_, int first, int last) {
 
 // ---- accept (optimizers.py:79-87) + table update -----------------------------------------------
 __global__ void lbfgs_accept(LbfgsDev* st_) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x != 0) return;
   const int count = st_->count, head = st_->head;
   const int pnew = (head + count) % SLOTS;
@@ -261,6 +269,8 @@ __global__ void lbfgs_coefficients(LbfgsDev* st_, double n_total) {
   // operations on one thread (global-memory latency per operand made this kernel 14 us, now ~3)
   __shared__ LbfgsDev sh;
   static_assert(sizeof(LbfgsDev) % 8 == 0, "LbfgsDev is copied as doubles");
+  pdl_trigger();
+  pdl_wait();
   {
     const double* src = reinterpret_cast<const double*>(st_);
     double* dst = reinterpret_cast<double*>(&sh);
@@ -308,6 +318,8 @@ template <int V>
 __global__ void __launch_bounds__(kThreads, 1)
 lbfgs_pass_b(LbfgsDev* st_, float* __restrict__ S, const float* __restrict__ Y, const float* __restrict__ g,
              float* __restrict__ x, long long n, float step) {
+  pdl_trigger();
+  pdl_wait();
   const int count = st_->count, head = st_->head;
   const int pnew = (head + count) % SLOTS;
   float* s_new = S + (long long)pnew * n;
@@ -377,8 +389,8 @@ struct st2_lbfgs {
 
 #define LAUNCH_V(kernel, grid, ...)                                                             \
   do {                                                                                          \
-    if (o->n % 4 == 0) kernel<4><<<grid, kThreads, 0, s>>>(__VA_ARGS__);                        \
-    else kernel<1><<<grid, kThreads, 0, s>>>(__VA_ARGS__);                                      \
+    if (o->n % 4 == 0) st2_launch_pdl(ctx, true, kernel<4>, grid, kThreads, 0, __VA_ARGS__);    \
+    else st2_launch_pdl(ctx, true, kernel<1>, grid, kThreads, 0, __VA_ARGS__);                  \
     ST2_LAUNCH_CHECK(ctx);                                                                      \
   } while (0)
 
@@ -444,7 +456,7 @@ int st2_lbfgs_advance_end(st2_lbfgs* o, float* x, const float* g, float step) {
     lbfgs_take_g<<<1, 32, 0, s>>>(o->st);
     ST2_LAUNCH_CHECK(ctx);
   }
-  lbfgs_coefficients<<<1, 128, 0, s>>>(o->st, o->n_total);
+  st2_launch_pdl(ctx, true, lbfgs_coefficients, 1, 128, 0, o->st, o->n_total);
   ST2_LAUNCH_CHECK(ctx);
   LAUNCH_V(lbfgs_pass_b, grid_for(o->n, ctx->sm_count), o->st, o->S, o->Y, g, x, o->n, step);
   o->have_gdots = false;
@@ -477,7 +489,7 @@ int st2_lbfgs_commit_end(st2_lbfgs* o) {
   if (!o) return ST2_ERR_ARG;
   st2_ctx* ctx = o->ctx;
   ProfScope ps(ctx, 7);
-  lbfgs_accept<<<1, 32, 0, ctx->stream>>>(o->st);
+  st2_launch_pdl(ctx, true, lbfgs_accept, 1, 32, 0, o->st);
   ST2_LAUNCH_CHECK(ctx);
   o->have_gdots = true;
   return 0;

@@ -99,6 +99,8 @@ __device__ __forceinline__ bool w_on(float w) { return fabsf(w) > 1e-15f; }   //
 
 // zero the per-evaluation accumulators, keep norms / valid flags
 __global__ void clear_volatile_kernel(double* scal) {
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < ST2_SCAL_TOTAL; i += blockDim.x) {
     if (i >= ST2_SCAL_GLOBAL_BASE) { scal[i] = 0.0; continue; }
     const int f = i % ST2_SCAL_PER_BLOB;
@@ -108,6 +110,8 @@ __global__ void clear_volatile_kernel(double* scal) {
 
 // fp16 copy of D scaled by a power of two chosen from rms(D): |D'| <= ~1, |D' F| <= ~max|F|
 __global__ void style_scale_kernel(const float* __restrict__ D, __half* __restrict__ Dh, int C, double* sb) {
+  pdl_trigger();
+  pdl_wait();
   const double n = (double)C * C;
   const double rms = sqrt(sb[SB_S_GRAMSQ] / n);
   float ds = 1.0f;
@@ -137,6 +141,8 @@ style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, cons
   // sum_p |D' F_p|^2 to the all-reduced total (like a strip that does not fold); nullptr: the whole canvas,
   // F^T F = (D + A) C HW.
   constexpr int C = 64;
+  pdl_trigger();
+  pdl_wait();
   const double rms = sqrt(sb[SB_S_GRAMSQ] / (double)(C * C));
   float ds = 1.0f;
   if (rms > 0.0 && isfinite(rms)) ds = exp2f(-ceilf(log2f((float)rms * (float)C)));
@@ -171,6 +177,8 @@ style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, cons
 __global__ void __launch_bounds__(256)
 style_rawsq_kernel(const float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ gsum_local, int C,
                    double n_total, const double* sb, double* raw_sum) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double tot = 0.0;
   if (idx < (long long)C * C) {
@@ -206,6 +214,8 @@ __global__ void stencil_pack_kernel(const __half* __restrict__ wbwd, __half* __r
 // combine coefficients only, from the FROZEN normalisers (the sums are not reduced yet; a normaliser that is not
 // frozen is a protocol error and raises the sticky flag); mode 2 after the merged all-reduce -- the trace values.
 __global__ void coef_kernel(EvalSpec es, double* scal, int mode) {
+  pdl_trigger();
+  pdl_wait();
   const int k = threadIdx.x;
   if (k >= es.n) return;
   const int b = es.order[k];
@@ -260,6 +270,8 @@ __global__ void coef_kernel(EvalSpec es, double* scal, int mode) {
 
 // worker.py:279-301: totals in the reference's accumulation order
 __global__ void final_kernel(EvalSpec es, double* scal, const int* halo_err) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double* g = scal + ST2_SCAL_GLOBAL_BASE;
   g[ST2_G_HALO_TIMEOUT] = (halo_err != nullptr && *halo_err != 0) ? 1.0 : 0.0;
@@ -830,7 +842,7 @@ static int eval_begin_impl(st2_plan* pl, const float* x, int want_grad) {
   es.N = pl->b[0].n_total();
   pl->eval_top = top; pl->eval_want_grad = want_grad; pl->eval_x = x;
 
-  clear_volatile_kernel<<<1, 256, 0, ctx->stream>>>(pl->scal);
+  st2_launch_pdl(ctx, true, clear_volatile_kernel, 1, 256, 0, pl->scal);
   ST2_LAUNCH_CHECK(ctx);
   if (pl->strip) ST2_CUDA(ctx, cudaMemsetAsync(pl->red, 0, sizeof(double) * 3 * ST2_NUM_BLOBS, ctx->stream));
   int rc = forward_impl<T>(pl, x, top);
@@ -942,8 +954,8 @@ static int eval_mid_impl(st2_plan* pl) {
                      : tc_conv_dual_plan_create(ctx, gsrc, asrc, B.wfold, B.H, B.W, &B.tc_sfold, pl->strip ? 1 : 0);
         if (rc) return rc;
       }
-      style_fold_kernel<<<32, 128, 0, ctx->stream>>>(B.D, B.gram_target, pl->strip ? pl->gram_local[1] : nullptr,
-                                                     ctx->w_oihw[0], B.wfold, stencil ? 1 : 0, B.n_total(), sb, raw_sum);
+      st2_launch_pdl(ctx, true, style_fold_kernel, 32, 128, 0, B.D, B.gram_target, pl->strip ? pl->gram_local[1] : nullptr,
+                     ctx->w_oihw[0], B.wfold, stencil ? 1 : 0, B.n_total(), sb, raw_sum);
       ST2_LAUNCH_CHECK(ctx);
       pl->inj[b].sraw = nullptr;
       pl->inj[b].fold = true;
@@ -956,10 +968,10 @@ static int eval_mid_impl(st2_plan* pl) {
         if ((rc = tc_conv_set_style_fuse(ctx, above, (const __half*)(pl->strip ? B.act_pad : B.act), B.Dh))) return rc;
         B.dfuse_set = true;
       }
-      style_scale_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(B.D, B.Dh, B.C, sb);
+      st2_launch_pdl(ctx, true, style_scale_kernel, cdiv((long long)B.C * B.C, 256), 256, 0, B.D, B.Dh, B.C, sb);
       ST2_LAUNCH_CHECK(ctx);
-      style_rawsq_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(
-          B.D, B.gram_target, pl->strip ? pl->gram_local[b] : nullptr, B.C, B.n_total(), sb, raw_sum);
+      st2_launch_pdl(ctx, true, style_rawsq_kernel, cdiv((long long)B.C * B.C, 256), 256, 0, B.D, B.gram_target,
+                     pl->strip ? pl->gram_local[b] : nullptr, B.C, B.n_total(), sb, raw_sum);
       ST2_LAUNCH_CHECK(ctx);
       pl->inj[b].sraw = nullptr;
       pl->inj[b].dfuse = true;
@@ -973,7 +985,7 @@ static int eval_mid_impl(st2_plan* pl) {
         if (!B.tc_style &&
             (rc = tc_conv_plan_create(ctx, (const __half*)B.act, B.Dh, B.H, B.W, B.C, B.C, 1, &B.tc_style)))
           return rc;
-        style_scale_kernel<<<cdiv((long long)B.C * B.C, 256), 256, 0, ctx->stream>>>(B.D, B.Dh, B.C, sb);
+        st2_launch_pdl(ctx, true, style_scale_kernel, cdiv((long long)B.C * B.C, 256), 256, 0, B.D, B.Dh, B.C, sb);
         ST2_LAUNCH_CHECK(ctx);
         rc = tc_conv_launch(ctx, B.tc_style, nullptr, nullptr, (__half*)B.sraw, EPI_RAW, 1.f, raw_sum);
       } else {
@@ -1008,7 +1020,7 @@ static int eval_end_impl(st2_plan* pl, float* grad_out) {
   }
   if (es.n > 0) {
     ProfScope ps(ctx, 5);
-    coef_kernel<<<1, 32, 0, ctx->stream>>>(es, pl->scal, pl->eval_deferred ? 1 : 0);
+    st2_launch_pdl(ctx, true, coef_kernel, 1, 32, 0, es, pl->scal, pl->eval_deferred ? 1 : 0);
     ST2_LAUNCH_CHECK(ctx);
   }
   double* gscal = pl->scal + ST2_SCAL_GLOBAL_BASE;
@@ -1045,11 +1057,12 @@ static int eval_final_impl(st2_plan* pl) {
     scatter_sums_kernel<<<1, 32, 0, ctx->stream>>>(pl->red, pl->scal);
     ST2_LAUNCH_CHECK(ctx);
     if (pl->es.n > 0) {
-      coef_kernel<<<1, 32, 0, ctx->stream>>>(pl->es, pl->scal, 2);
+      st2_launch_pdl(ctx, true, coef_kernel, 1, 32, 0, pl->es, pl->scal, 2);
       ST2_LAUNCH_CHECK(ctx);
     }
   }
-  final_kernel<<<1, 32, 0, ctx->stream>>>(pl->es, pl->scal, pl->strip ? &reinterpret_cast<SlabHeader*>(pl->slab)->err : nullptr);
+  st2_launch_pdl(ctx, true, final_kernel, 1, 32, 0, pl->es, pl->scal,
+                 pl->strip ? &reinterpret_cast<SlabHeader*>(pl->slab)->err : nullptr);
   ST2_LAUNCH_CHECK(ctx);
   pl->eval_phase = 0;
   return 0;
@@ -1101,6 +1114,7 @@ int st2_ctx_create(int device, st2_ctx** out) {
     k.no_inkernel_halo = getenv("ST2_NO_INKERNEL_HALO") != nullptr;
     k.no_stencil = getenv("ST2_NO_STENCIL") != nullptr;
     k.no_ws128 = getenv("ST2_NO_WS128") != nullptr;
+    k.no_pdl = getenv("ST2_NO_PDL") != nullptr;
     if (const char* v = getenv("ST2_TC_BN")) k.tc_bn = atoi(v);
     if (const char* v = getenv("ST2_PAIR_MIN_TILES")) k.pair_min_tiles = atoll(v);
   }

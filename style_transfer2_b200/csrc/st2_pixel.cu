@@ -66,6 +66,8 @@ pixel_terms_kernel(const float* __restrict__ x, const float* __restrict__ bwd, f
   // Sums: per-block partials -> `part` -> summed by the last block to finish (one writer per scalar instead of
   // six same-line fp64 atomics per block); part == nullptr: plain atomics (stand-alone st2_pixel_terms).
   __shared__ float sv[kPxRows + 2][kPxCols + 2];
+  pdl_trigger();
+  pdl_wait();
   const long long HW = (long long)H * W;
   const float half_beta = beta * 0.5f;
   const int m_norm = (TVM == 0 || half_beta == 1.0f) ? 1 : 2;
@@ -255,8 +257,8 @@ int pixel_terms_strip(st2_ctx* ctx, const float* x, long long xps, int wrap, con
   if (blocks > ctx->sm_count * 5) blocks = ctx->sm_count * 5;
   if (blocks > ST2_PART_BLOCKS) blocks = ST2_PART_BLOCKS;
 #define ST2_PIXEL_LAUNCH(TVM, PI)                                                                                    \
-  pixel_terms_kernel<TVM, PI><<<blocks, kThreads, 0, ctx->stream>>>(x, bwd, grad_out, C, H, W, xps, wrap, tv, tv_power, p, \
-                                                                    p_power, divisor, scal, part, counter)
+  st2_launch_pdl(ctx, true, pixel_terms_kernel<TVM, PI>, blocks, kThreads, 0, x, bwd, grad_out, C, H, W, xps, wrap, tv,    \
+                 tv_power, p, p_power, divisor, scal, part, counter)
   const bool b2 = tv_power == 2.0f;
   if (p_power == 6.0f) { if (b2) ST2_PIXEL_LAUNCH(0, 6); else ST2_PIXEL_LAUNCH(1, 6); }
   else if (p_power == 2.0f) { if (b2) ST2_PIXEL_LAUNCH(0, 2); else ST2_PIXEL_LAUNCH(1, 2); }
