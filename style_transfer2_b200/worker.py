@@ -618,6 +618,7 @@ class StyleTransfer:
 
     def close(self):
         """Release the plans this job owns (private_plans=True)."""
+        self._drop_graphs()
         if self._private_plans:
             for plan in self._private_plans.values():
                 self.model.release_plan(plan)
