@@ -227,7 +227,20 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 // few steps (pixels at +-11 000) and recovers; an inf in an activation would instead
 // poison every later iterate with NaN.
 __device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
-__device__ __forceinline__ __half2 h2_sat(float a, float b) { return __floats2half2_rn(sat_h(a), sat_h(b)); }
+// (a, b) -> half2 {lo: a, hi: b}, finite-saturating, in ONE instruction (F2FP.SATFINITE...PACK_AB): the epilogues of the
+// convolution kernels are bound by their instruction count (one warp per scheduler), and clamping in fp32 first cost
+// four FMNMX per pair.  |v| > 65504 (and +-inf) -> +-65504 as before; a NaN stays a NaN.
+__device__ __forceinline__ __half2 h2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return *reinterpret_cast<__half2*>(&r);
+}
+// the same with max(v, 0) folded in (ReLU epilogues)
+__device__ __forceinline__ __half2 h2_relu_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return *reinterpret_cast<__half2*>(&r);
+}
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(sat_h(v)); }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

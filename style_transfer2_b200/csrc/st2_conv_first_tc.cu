@@ -85,10 +85,10 @@ __device__ __forceinline__ void epi_chunk_first(const uint32_t (&r)[32], const f
     const float4 b0 = __ldg(bp + 2 * q), b1 = __ldg(bp + 2 * q + 1);
     uint4 o;
     __half2* hp = reinterpret_cast<__half2*>(&o);
-    hp[0] = h2_sat(fmaxf(__uint_as_float(r[8 * q + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(r[8 * q + 1]) + b0.y, 0.f));
-    hp[1] = h2_sat(fmaxf(__uint_as_float(r[8 * q + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(r[8 * q + 3]) + b0.w, 0.f));
-    hp[2] = h2_sat(fmaxf(__uint_as_float(r[8 * q + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(r[8 * q + 5]) + b1.y, 0.f));
-    hp[3] = h2_sat(fmaxf(__uint_as_float(r[8 * q + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(r[8 * q + 7]) + b1.w, 0.f));
+    hp[0] = h2_relu_sat(__uint_as_float(r[8 * q + 0]) + b0.x, __uint_as_float(r[8 * q + 1]) + b0.y);
+    hp[1] = h2_relu_sat(__uint_as_float(r[8 * q + 2]) + b0.z, __uint_as_float(r[8 * q + 3]) + b0.w);
+    hp[2] = h2_relu_sat(__uint_as_float(r[8 * q + 4]) + b1.x, __uint_as_float(r[8 * q + 5]) + b1.y);
+    hp[3] = h2_relu_sat(__uint_as_float(r[8 * q + 6]) + b1.z, __uint_as_float(r[8 * q + 7]) + b1.w);
     op[(((sw >> 3) & 7) + q) ^ (sw & 7)] = o;
   }
 }

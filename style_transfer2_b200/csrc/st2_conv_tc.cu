@@ -182,15 +182,34 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (epi == EPI_BIAS_RELU) {
+  uint4 o4[4];
+  // The two common forms first, in packed fp16 arithmetic (the epilogue warps are bound by their instruction count):
+  // bias + ReLU + saturation = one add and half a convert per value; a bare ReLU mask = half a convert, half a
+  // compare and half an AND.  Both give the bits of the fp32 forms below.
+  const bool fast_relu = epi == EPI_BIAS_RELU;
+  const bool fast_mask = epi == EPI_MASK && !have_inj && r2 == nullptr;
+  if (fast_relu) {
     const float4* bp = reinterpret_cast<const float4*>(bias_c);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b = __ldg(bp + q);
-      v[4 * q + 0] = fmaxf(v[4 * q + 0] + b.x, 0.f);
-      v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y, 0.f);
-      v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z, 0.f);
-      v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w, 0.f);
+    for (int q = 0; q < 4; ++q) {
+      const float4 b0 = __ldg(bp + 2 * q), b1 = __ldg(bp + 2 * q + 1);
+      __half2* hp = reinterpret_cast<__half2*>(&o4[q]);
+      hp[0] = h2_relu_sat(v[8 * q + 0] + b0.x, v[8 * q + 1] + b0.y);
+      hp[1] = h2_relu_sat(v[8 * q + 2] + b0.z, v[8 * q + 3] + b0.w);
+      hp[2] = h2_relu_sat(v[8 * q + 4] + b1.x, v[8 * q + 5] + b1.y);
+      hp[3] = h2_relu_sat(v[8 * q + 6] + b1.z, v[8 * q + 7] + b1.w);
+    }
+  } else if (fast_mask) {
+    const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __half2* hp = reinterpret_cast<const __half2*>(&a4[q]);
+      uint32_t* op = reinterpret_cast<uint32_t*>(&o4[q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 h = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+        op[e] = *reinterpret_cast<const uint32_t*>(&h) & __hgt2_mask(hp[e], zero);
+      }
     }
   } else if (epi == EPI_MASK) {
 #pragma unroll
@@ -247,12 +266,13 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
       for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
     }
   }
-  uint4 o4[4];
+  if (!fast_relu && !fast_mask) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    __half2* hp = reinterpret_cast<__half2*>(&o4[q]);
+    for (int q = 0; q < 4; ++q) {
+      __half2* hp = reinterpret_cast<__half2*>(&o4[q]);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+      for (int e = 0; e < 4; ++e) hp[e] = h2_sat(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+    }
   }
   if (po.p != nullptr || po.vert != 0) {
     // Caffe's ceil-mode 2x2/2 max pool of the post-ReLU output, first in registers: the window's other pixels sit in

@@ -98,7 +98,7 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
           __half2* hp = reinterpret_cast<__half2*>(&u);
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            hp[e] = h2_sat(fmaxf(a[8 * q + 2 * e], 0.f), fmaxf(a[8 * q + 2 * e + 1], 0.f));
+            hp[e] = h2_relu_sat(a[8 * q + 2 * e], a[8 * q + 2 * e + 1]);
           row[(half * 4 + q) ^ (px & 7)] = u;
         }
         __syncthreads();
