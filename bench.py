@@ -316,6 +316,36 @@ def profile_categories(eng, step, n, extra=None):
     return cats
 
 
+def back_to_back_layers(st, size, peaks, reps=20):
+    """The 24 convolution launches of the roofline family one layer at a time: `reps` launches of the same kernel between
+    ONE pair of CUDA events (st2_bench_layer), i.e. each kernel's average launch duration without an event pair around
+    every launch and with its successor's prologue overlapping its tail, as in the graph-replayed iteration.  The small
+    layers find their operands in L2, as they do inside the iteration (their producer just wrote them)."""
+    import ctypes as C
+    from style_transfer2_b200 import vgg
+    plan = st._plan
+    burst, sustained = peaks.get('bf16_tflops', 1650.0), peaks.get('bf16_tflops_sustained', 1400.0)
+    rows, tot_ms, tot_fl = [], 0.0, 0.0
+    for b in range(2, vgg.BLOB_INDEX['conv5_1'] + 1):
+        name, kind, cout = vgg.TOPOLOGY[b]
+        if kind != 'conv':
+            continue
+        cin = vgg.TOPOLOGY[b - 1][2]
+        _, h, w = plan.blob_dims(b)
+        fl = 18.0 * cin * cout * h * w
+        for d, tag in ((0, 'fwd'), (1, 'dgrad')):
+            ms = C.c_float()
+            plan._check(plan.lib.st2_bench_layer(plan.handle, b, d, reps, C.byref(ms)), 'st2_bench_layer')
+            rows.append({'layer': name, 'dir': tag, 'us': round(ms.value * 1e3, 2), 'tflops': round(fl / (ms.value * 1e-3) / 1e12, 1)})
+            tot_ms += ms.value
+            tot_fl += fl
+    ach = tot_fl / (tot_ms * 1e-3) / 1e12
+    return {'ms_total': tot_ms, 'achieved': ach, 'unit': 'TFLOP/s', 'frac_of_burst_peak': ach / burst,
+            'frac_of_sustained_peak': ach / sustained, 'launches': len(rows), 'reps_per_launch': reps, 'layers': rows,
+            'note': 'same 24 kernels, each timed as %d back-to-back launches between one pair of CUDA events '
+                    '(plain epilogues: no fused pool / loss injection)' % reps}
+
+
 def rooflines_of(cats, size, share, peaks, regime, precision, canvas=False):
     """The dominant tensor-core family first (the line's `roofline`), then one entry per bandwidth-bound category."""
     out = []
@@ -770,6 +800,12 @@ def main():
         line['sustained'] = {'seconds': ms_s / 1000.0, 'steps': n_sus, 'value': jobs * n_sus / (ms_s / 1000.0), 'unit': 'it/s',
                              'ms_per_step': ms_s / n_sus, 'clocks': c_s, 'roofline': r_s,
                              'note': 'back-to-back iterations for >= %.0f s; category times taken from the 20 iterations right after' % args.sustained_seconds}
+
+    if world == 1 and not canvas and args.precision == 'fp16' and size == 1024:
+        try:                               # explanatory figure next to `roofline`: never lose the line over it
+            line['roofline']['back_to_back'] = back_to_back_layers(st, size, peaks)
+        except Exception as exc:
+            line['roofline']['back_to_back'] = {'error': repr(exc)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         its, cores, sample, _, cpu_first = run_cpu_reference(size, 6, 1, args.cpu_budget, first_eval=want_parity)
