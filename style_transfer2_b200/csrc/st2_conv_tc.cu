@@ -1038,9 +1038,10 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         continue;
       }
       uint4 pa[NCH][4], ps[NCH][4];
-      if (masked) {
+      if (masked && (!mtma || have_s)) {
         // pull the NEXT tile's epilogue operands towards L2 now: per tile the loads below are issued and then
-        // immediately needed, so their latency (not their bandwidth) is what the epilogue pays
+        // immediately needed, so their latency (not their bandwidth) is what the epilogue pays (a TMA-fetched mask
+        // tile is a tile ahead anyway)
         const int ptn = pt + pt_step;
         if (ptn < n_pt) {
           const int thns = ptn / g.tiles_w, twn = ptn - thns * g.tiles_w;
@@ -1048,7 +1049,7 @@ tc_conv_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int hn = thn * kWsTH + row_h, wn = twn * kWsTW + row_w;
           if (hn < g.H && wn < g.W) {
             const long long on = ((long long)hn * g.W + wn) * g.cout + (long long)nb * BN;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(act + on));
+            if (!mtma) asm volatile("prefetch.global.L2 [%0];" ::"l"(act + on));
             if (have_s) asm volatile("prefetch.global.L2 [%0];" ::"l"(inj.sraw + on));
           }
         }

@@ -152,7 +152,8 @@ style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, cons
     const int j = idx % C, tapf = (idx / C) % 9, plane = idx / (9 * C);
     const int r = 2 - tapf / 3, sx = 2 - tapf % 3;              // tap' = flipped tap of the forward weights
     float acc = 0.f;
-#pragma unroll 8
+    // (unroll 32: every unrolled group of rows is one L2 round trip for the whole warp, and the groups are serial)
+#pragma unroll 32
     for (int i = 0; i < C; ++i) acc = fmaf(__ldg(w_oihw + ((i * 3 + plane) * 3 + r) * 3 + sx), __ldg(D + i * C + j), acc);
     // stencil_layout: [source 1][row = tap' * 3 + plane][64]; else the dual pack [plane][tap'][128], channels 64..127
     if (stencil_layout) wdual[(32 + tapf * 3 + plane) * C + j] = __float2half_rn(acc * ds);
@@ -162,13 +163,17 @@ style_fold_kernel(const float* __restrict__ D, const float* __restrict__ A, cons
   if (idx < C * C) {
     const int j = idx / C, k = idx % C;
     double e = 0.0;
-#pragma unroll 8
+#pragma unroll 32
     for (int i = 0; i < C; ++i) e += (double)__ldg(D + i * C + j) * (double)__ldg(D + i * C + k);
     tot = gsum_local != nullptr ? e * (double)gsum_local[idx]
                                 : e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0)) * n_total;
   }
+  // one atomic per block: same-address fp64 atomics serialise in L2, and the kernel's end waits for all of them
+  __shared__ double red[4];
   tot = warp_sum_d(tot);
-  if ((threadIdx.x & 31) == 0) atomicAdd(raw_sum, tot * (double)ds * (double)ds);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(raw_sum, (red[0] + red[1] + red[2] + red[3]) * (double)ds * (double)ds);
 }
 
 // sum_p |D' F_p|^2 = <D'^T D', F^T F> for a style layer whose gradient is never materialised (see above; ds is read
@@ -184,14 +189,22 @@ style_rawsq_kernel(const float* __restrict__ D, const float* __restrict__ A, con
   if (idx < (long long)C * C) {
     const int j = (int)(idx / C), k = (int)(idx % C);
     double e = 0.0;
-#pragma unroll 8
+#pragma unroll 32
     for (int i = 0; i < C; ++i) e += (double)__ldg(D + (long long)i * C + j) * (double)__ldg(D + (long long)i * C + k);
     tot = gsum_local != nullptr ? e * (double)gsum_local[idx]
                                 : e * ((double)D[idx] + (A != nullptr ? (double)A[idx] : 0.0)) * n_total;
   }
+  __shared__ double red[8];
   tot = warp_sum_d(tot);
-  const double ds = sb[SB_S_DSCALE];
-  if ((threadIdx.x & 31) == 0 && tot != 0.0) atomicAdd(raw_sum, tot * ds * ds);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const double ds = sb[SB_S_DSCALE];
+    if (t != 0.0) atomicAdd(raw_sum, t * ds * ds);
+  }
 }
 
 // conv1_1 data-gradient weights [16][9][64] -> the gradient-channel half of the dual pack [16][9][128]
