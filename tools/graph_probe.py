@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Experiment: how much of an iteration is launch gaps?  Times K L-BFGS steps enqueued normally and the same steps
-replayed from a CUDA graph (two steps per graph: the gradient double buffer alternates).  usage: python tools/graph_probe.py [size]"""
+replayed from a CUDA graph (two steps per graph: the gradient double buffer alternates).  This was the experiment behind
+StyleTransfer._graph_step (worker.py), which is what production steps use now.  usage: python tools/graph_probe.py [size]"""
 import os
 import sys
 
@@ -11,6 +12,7 @@ import bench
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 st, _ = bench.build_job(size, 'fp16')
+st.use_graphs = False          # the experiment compares plain enqueueing with its own capture (StyleTransfer now replays graphs itself)
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):
     for _ in range(6):
