@@ -570,10 +570,18 @@ class StyleTransfer:
         if self._graphs is None:
             if self._stable_steps < 3 or self._weights_dirty or self._pending_norms:
                 return False
-            self._graph_capture()
+            try:
+                self._graph_capture()
+            except Exception:                  # never lose a job over the fast path: go on kernel by kernel
+                logging.getLogger(__name__).exception('CUDA graph capture failed; continuing without graphs')
+                self.use_graphs = False
+                self._graphs = None
+                self.engine.sync_stream()
+                opt.objective_changed()        # libst2's step bookkeeping may be mid-sequence: start a clean history
+                return False
         g = self._graphs
-        if (g['plan'] is not self._plan or g['step_size'] != opt.step_size or opt.grad is not g['g0']
-                or g['x'] is not self.input or opt.x is not self.input):
+        if (g['plan'] is not self._plan or not g['plan'].handle or g['step_size'] != opt.step_size
+                or opt.grad is not g['g0'] or g['x'] is not self.input or opt.x is not self.input):
             self._drop_graphs()
             return False
         k = g['turn']
