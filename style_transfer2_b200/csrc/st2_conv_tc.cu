@@ -187,7 +187,11 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const int epi
   // bias + ReLU + saturation = one add and half a convert per value; a bare ReLU mask = half a convert, half a
   // compare and half an AND.  Both give the bits of the fp32 forms below.
   const bool fast_relu = epi == EPI_BIAS_RELU;
-  const bool fast_mask = epi == EPI_MASK && !have_inj && r2 == nullptr;
+  // an injection with nothing to inject is a bare mask too: the launch above a style layer whose gradient is folded
+  // (conv1_2's data gradient, the most expensive launch of the iteration) carries the coefficient block but no content
+  // target, no style tensor and a zero deep-dream coefficient
+  const bool inj_active = have_inj && (fc_c != nullptr || have_s || dc != 0.f);
+  const bool fast_mask = epi == EPI_MASK && !inj_active && r2 == nullptr;
   if (fast_relu) {
     const float4* bp = reinterpret_cast<const float4*>(bias_c);
 #pragma unroll
